@@ -1,0 +1,456 @@
+// C-ABI entry points of the AR transformer engine (see include/llamagen_b200.h).
+//
+// Replaces, for inference only:
+//   autoregressive/models/gpt.py:316-330  Transformer.setup_caches   -> lg_engine_set_workspace
+//   autoregressive/models/gpt.py:341-368  Transformer.forward        -> Engine::forward
+//   autoregressive/models/generate.py:77-176 prefill/decode/generate -> lg_prefill / lg_decode_step / lg_generate
+// The decode loop never leaves the device: sampled tokens, the position and the step counter live in
+// HBM, so one captured CUDA graph of a decode step is replayed S-2 times with no host round trip.
+#include "kernels.cuh"
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+std::string& lg_err_slot() {
+    static thread_local std::string s;
+    return s;
+}
+int lg_fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    lg_err_slot() = buf;
+    return -1;
+}
+std::atomic<uint64_t> g_lg_launches{0};
+
+namespace {
+
+struct Tensor {
+    const void* p = nullptr;
+    int64_t shape[4] = {0, 0, 0, 0};
+    int ndim = 0;
+    int dtype = 0;
+};
+
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+    char* base = nullptr;
+    size_t bytes = 0;
+    int rows = 0, max_seq = 0;
+    // carved pointers
+    char *kcache = nullptr, *vcache = nullptr;
+    char *h = nullptr, *xn = nullptr, *q = nullptr, *attn = nullptr, *ff = nullptr, *x0 = nullptr;
+    float *partial = nullptr, *logits = nullptr;
+    int32_t* tokens = nullptr;
+    int* counters = nullptr;  // [0] = pos, [1] = step
+    size_t layer_cache_bytes = 0;
+};
+
+struct Layer {
+    const void *wqkv, *wo, *w1, *w3, *w2, *attn_norm, *ffn_norm;
+};
+
+}  // namespace
+
+struct lg_engine {
+    lg_model_cfg cfg;
+    int device = 0;
+    int hd = 0;
+    size_t esz = 2;
+    std::unordered_map<std::string, Tensor> w;
+    std::vector<Layer> layers;
+    const void *tok_emb = nullptr, *cls_table = nullptr, *cap_fc1 = nullptr, *cap_fc2 = nullptr, *uncond = nullptr;
+    const void *final_norm = nullptr, *output = nullptr;
+    const float* freqs = nullptr;
+    bool finalized = false;
+    Workspace ws;
+    bool use_graph = true;
+
+    size_t carve(Workspace& o, char* base, int rows, int max_seq) const;
+    int forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, float* logits_out, bool round_out,
+                cudaStream_t st);
+    int embed_cond(const void* cond, int B, int R, int T, cudaStream_t st);
+    int gemm(const void* x, int M, int N, int K, const void* wa, const void* wb, int n_split, int* ksplit,
+             float* direct_out, cudaStream_t st);
+};
+
+size_t lg_engine::carve(Workspace& o, char* base, int rows, int max_seq) const {
+    const int L = cfg.n_layer, D = cfg.dim, F = cfg.ffn_dim, V = cfg.vocab_size, H = cfg.n_head;
+    const int Tc = cfg.model_type == LG_MODEL_T2I ? cfg.cls_token_num : 1;
+    const size_t Mmax = (size_t)rows * Tc;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* p = base ? base + off : nullptr;
+        off += align_up(bytes);
+        return p;
+    };
+    o.layer_cache_bytes = (size_t)rows * H * max_seq * hd * esz;
+    o.kcache = take(o.layer_cache_bytes * L);
+    o.vcache = take(o.layer_cache_bytes * L);
+    o.h = take(Mmax * D * esz);
+    o.xn = take(Mmax * D * esz);
+    o.q = take(Mmax * D * esz);
+    o.attn = take(Mmax * D * esz);
+    o.ff = take(Mmax * F * esz);
+    o.x0 = take(cfg.model_type == LG_MODEL_T2I ? Mmax * cfg.caption_dim * esz : 0);
+    size_t pf = 0;
+    const int Ms[2] = {rows, (int)Mmax};
+    for (int i = 0; i < 2; ++i) {
+        const int M = Ms[i];
+        pf = std::max(pf, gemm_partial_floats(M, 3 * D, D, cfg.dtype));
+        pf = std::max(pf, gemm_partial_floats(M, D, D, cfg.dtype));
+        pf = std::max(pf, gemm_partial_floats(M, 2 * F, D, cfg.dtype));
+        pf = std::max(pf, gemm_partial_floats(M, D, F, cfg.dtype));
+        if (cfg.model_type == LG_MODEL_T2I) pf = std::max(pf, gemm_partial_floats(M, D, cfg.caption_dim, cfg.dtype));
+    }
+    pf = std::max(pf, gemm_partial_floats(rows, V, D, cfg.dtype));
+    o.partial = (float*)take(pf * sizeof(float));
+    o.logits = (float*)take((size_t)rows * V * sizeof(float));
+    o.tokens = (int32_t*)take((size_t)rows * sizeof(int32_t));
+    o.counters = (int*)take(2 * sizeof(int));
+    o.rows = rows;
+    o.max_seq = max_seq;
+    return off;
+}
+
+int lg_engine::gemm(const void* x, int M, int N, int K, const void* wa, const void* wb, int n_split, int* ksplit,
+                    float* direct_out, cudaStream_t st) {
+    // when the plan needs a single slab the GEMM can write straight into `direct_out`
+    const size_t slabs = gemm_partial_floats(M, N, K, cfg.dtype) / ((size_t)M * N);
+    float* dst = (direct_out && slabs == 1) ? direct_out : ws.partial;
+    GemmPlan plan;
+    LG_TRY(gemm_partial(x, K, wa, wb, n_split, M, N, K, cfg.dtype, dst, &plan, st));
+    *ksplit = plan.ksplit;
+    return dst == direct_out ? 1 : 0;
+}
+
+int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, float* logits_out, bool round_out,
+                       cudaStream_t st) {
+    const int L = cfg.n_layer, D = cfg.dim, F = cfg.ffn_dim, V = cfg.vocab_size, H = cfg.n_head;
+    const int R = M / Tq;
+    const int dt = cfg.dtype;
+    int ks = 1;
+    LG_TRY(launch_rmsnorm(ws.h, layers[0].attn_norm, ws.xn, M, D, cfg.norm_eps, dt, st));
+    for (int l = 0; l < L; ++l) {
+        const Layer& ly = layers[l];
+        char* kc = ws.kcache + (size_t)l * ws.layer_cache_bytes;
+        char* vc = ws.vcache + (size_t)l * ws.layer_cache_bytes;
+        LG_TRY(gemm(ws.xn, M, 3 * D, D, ly.wqkv, nullptr, 0, &ks, nullptr, st));
+        QkvEpiArgs qa;
+        qa.partial = ws.partial; qa.ksplit = ks; qa.M = M; qa.Tq = Tq; qa.D = D; qa.H = H; qa.hd = hd;
+        qa.pos = pos; qa.freqs = freqs; qa.q = ws.q; qa.kcache = kc; qa.vcache = vc; qa.maxS = ws.max_seq; qa.dtype = dt;
+        LG_TRY(launch_qkv_epilogue(qa, st));
+        AttnArgs aa;
+        aa.q = ws.q; aa.kcache = kc; aa.vcache = vc; aa.out = ws.attn; aa.R = R; aa.Tq = Tq; aa.H = H; aa.hd = hd;
+        aa.maxS = ws.max_seq; aa.pos = pos; aa.emb_mask = emb_mask; aa.B = B;
+        aa.Tc = cfg.cls_token_num; aa.scale = 1.0f / sqrtf((float)hd); aa.dtype = dt;
+        LG_TRY(launch_attention(aa, st));
+        LG_TRY(gemm(ws.attn, M, D, D, ly.wo, nullptr, 0, &ks, nullptr, st));
+        LG_TRY(launch_residual_norm(ws.partial, ks, M, D, ws.h, ly.ffn_norm, ws.xn, cfg.norm_eps, dt, st));
+        LG_TRY(gemm(ws.xn, M, 2 * F, D, ly.w1, ly.w3, F, &ks, nullptr, st));
+        LG_TRY(launch_silu_mul(ws.partial, ks, M, F, ws.ff, dt, st));
+        LG_TRY(gemm(ws.ff, M, D, F, ly.w2, nullptr, 0, &ks, nullptr, st));
+        const void* next_norm = (l + 1 < L) ? layers[l + 1].attn_norm : final_norm;
+        LG_TRY(launch_residual_norm(ws.partial, ks, M, D, ws.h, next_norm, ws.xn, cfg.norm_eps, dt, st));
+    }
+    // head on the last position only (generate.py:58 reads logits[:, -1])
+    const void* xlast = ws.xn;
+    if (Tq > 1) {
+        LG_TRY(launch_gather_last(ws.xn, R, Tq, D, dt, ws.q, st));
+        xlast = ws.q;
+    }
+    (void)round_out;
+    const int direct = gemm(xlast, R, V, D, output, nullptr, 0, &ks, logits_out, st);
+    if (direct < 0) return direct;
+    if (direct == 0) LG_TRY(launch_reduce_f32(ws.partial, ks, R, V, logits_out, st));
+    return 0;
+}
+
+int lg_engine::embed_cond(const void* cond, int B, int R, int T, cudaStream_t st) {
+    const int D = cfg.dim, dt = cfg.dtype;
+    if (cfg.model_type == LG_MODEL_C2I) {
+        // LabelEmbedder (gpt.py:78-83); null class = num_classes (generate.py:130)
+        return launch_embed(cls_table, (const int32_t*)cond, B, R, cfg.num_classes, D, dt, ws.h, st);
+    }
+    // CaptionEmbedder: cap_proj = fc2(gelu_tanh(fc1(x))) (gpt.py:110-131); uncond rows = uncond_embedding
+    const int C = cfg.caption_dim, M = R * T;
+    int ks = 1;
+    LG_TRY(launch_build_caption_rows(cond, uncond, B, R, T, C, dt, ws.x0, st));
+    LG_TRY(gemm(ws.x0, M, D, C, cap_fc1, nullptr, 0, &ks, nullptr, st));
+    LG_TRY(launch_store_act(ws.partial, ks, M, D, ws.attn, 1, dt, st));
+    LG_TRY(gemm(ws.attn, M, D, D, cap_fc2, nullptr, 0, &ks, nullptr, st));
+    LG_TRY(launch_store_act(ws.partial, ks, M, D, ws.h, 0, dt, st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int lg_version(void) { return LG_ABI_VERSION; }
+const char* lg_last_error(void) { return lg_err_slot().c_str(); }
+uint64_t lg_launch_count(void) { return g_lg_launches.load(); }
+void lg_reset_launch_count(void) { g_lg_launches.store(0); }
+
+int lg_engine_create(const lg_model_cfg* cfg, int device, lg_engine** out) {
+    LG_REQUIRE(cfg && out, "lg_engine_create: null argument");
+    LG_REQUIRE(cfg->dtype == LG_DTYPE_F32 || cfg->dtype == LG_DTYPE_BF16, "unsupported dtype %d (f32 and bf16 only)", cfg->dtype);
+    LG_REQUIRE(cfg->model_type == LG_MODEL_C2I || cfg->model_type == LG_MODEL_T2I, "please check model type");
+    LG_REQUIRE(cfg->n_layer > 0 && cfg->n_head > 0 && cfg->dim > 0 && cfg->dim % cfg->n_head == 0, "bad model dims");
+    const int hd = cfg->dim / cfg->n_head;
+    LG_REQUIRE(hd == 64 || hd == 100 || hd == 128, "unsupported head_dim %d (64, 100, 128)", hd);
+    LG_REQUIRE(cfg->dim % 8 == 0 && cfg->ffn_dim % 8 == 0 && cfg->vocab_size % 2 == 0, "dims must be multiples of 8");
+    lg_engine* e = new lg_engine();
+    e->cfg = *cfg;
+    e->device = device;
+    e->hd = hd;
+    e->esz = cfg->dtype == LG_DTYPE_F32 ? 4 : 2;
+    const char* ng = getenv("LG_NO_GRAPH");
+    e->use_graph = !(ng && ng[0] == '1');
+    *out = e;
+    return 0;
+}
+
+void lg_engine_destroy(lg_engine* e) { delete e; }
+
+int lg_engine_bind_weight(lg_engine* e, const char* name, const void* dev_ptr, const int64_t* shape, int ndim,
+                          int dtype) {
+    LG_REQUIRE(e && name && dev_ptr && shape && ndim >= 1 && ndim <= 4, "lg_engine_bind_weight: bad argument");
+    Tensor t;
+    t.p = dev_ptr;
+    t.ndim = ndim;
+    t.dtype = dtype;
+    for (int i = 0; i < ndim; ++i) t.shape[i] = shape[i];
+    e->w[name] = t;
+    e->finalized = false;
+    return 0;
+}
+
+static int need(lg_engine* e, const std::string& name, int dtype, std::initializer_list<int64_t> shape,
+                const void** out) {
+    auto it = e->w.find(name);
+    LG_REQUIRE(it != e->w.end(), "missing weight '%s'", name.c_str());
+    const Tensor& t = it->second;
+    LG_REQUIRE(t.dtype == dtype, "weight '%s' has dtype %d, expected %d", name.c_str(), t.dtype, dtype);
+    LG_REQUIRE(t.ndim == (int)shape.size(), "weight '%s' has %d dims, expected %d", name.c_str(), t.ndim, (int)shape.size());
+    int i = 0;
+    for (int64_t s : shape) {
+        LG_REQUIRE(t.shape[i] == s, "weight '%s' dim %d is %lld, expected %lld", name.c_str(), i, (long long)t.shape[i], (long long)s);
+        ++i;
+    }
+    LG_REQUIRE(((uintptr_t)t.p & 15) == 0, "weight '%s' is not 16-byte aligned", name.c_str());
+    *out = t.p;
+    return 0;
+}
+
+int lg_engine_finalize(lg_engine* e) {
+    LG_REQUIRE(e, "null engine");
+    const lg_model_cfg& c = e->cfg;
+    const int D = c.dim, F = c.ffn_dim, V = c.vocab_size, dt = c.dtype;
+    e->layers.resize(c.n_layer);
+    for (int l = 0; l < c.n_layer; ++l) {
+        const std::string p = "layers." + std::to_string(l) + ".";
+        Layer& ly = e->layers[l];
+        LG_TRY(need(e, p + "attention.wqkv.weight", dt, {3 * D, D}, &ly.wqkv));
+        LG_TRY(need(e, p + "attention.wo.weight", dt, {D, D}, &ly.wo));
+        LG_TRY(need(e, p + "feed_forward.w1.weight", dt, {F, D}, &ly.w1));
+        LG_TRY(need(e, p + "feed_forward.w3.weight", dt, {F, D}, &ly.w3));
+        LG_TRY(need(e, p + "feed_forward.w2.weight", dt, {D, F}, &ly.w2));
+        LG_TRY(need(e, p + "attention_norm.weight", dt, {D}, &ly.attn_norm));
+        LG_TRY(need(e, p + "ffn_norm.weight", dt, {D}, &ly.ffn_norm));
+    }
+    LG_TRY(need(e, "tok_embeddings.weight", dt, {V, D}, &e->tok_emb));
+    LG_TRY(need(e, "norm.weight", dt, {D}, &e->final_norm));
+    LG_TRY(need(e, "output.weight", dt, {V, D}, &e->output));
+    if (c.model_type == LG_MODEL_C2I) {
+        auto it = e->w.find("cls_embedding.embedding_table.weight");
+        LG_REQUIRE(it != e->w.end(), "missing weight 'cls_embedding.embedding_table.weight'");
+        LG_REQUIRE(it->second.dtype == dt && it->second.ndim == 2 && it->second.shape[1] == D &&
+                       it->second.shape[0] > c.num_classes,
+                   "cls_embedding.embedding_table.weight must be [>num_classes, dim] (needs the CFG null row)");
+        e->cls_table = it->second.p;
+    } else {
+        LG_TRY(need(e, "cls_embedding.cap_proj.fc1.weight", dt, {D, c.caption_dim}, &e->cap_fc1));
+        LG_TRY(need(e, "cls_embedding.cap_proj.fc2.weight", dt, {D, D}, &e->cap_fc2));
+        LG_TRY(need(e, "cls_embedding.uncond_embedding", dt, {c.cls_token_num, c.caption_dim}, &e->uncond));
+    }
+    const void* fr = nullptr;
+    LG_TRY(need(e, "freqs_cis", LG_DTYPE_F32, {c.cls_token_num + c.block_size, e->hd / 2, 2}, &fr));
+    e->freqs = (const float*)fr;
+    e->finalized = true;
+    return 0;
+}
+
+int lg_engine_workspace_bytes(lg_engine* e, int rows, int max_seq, size_t* bytes) {
+    LG_REQUIRE(e && bytes && rows > 0 && max_seq > 0, "lg_engine_workspace_bytes: bad argument");
+    Workspace tmp;
+    *bytes = e->carve(tmp, nullptr, rows, max_seq);
+    return 0;
+}
+
+int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, int max_seq) {
+    LG_REQUIRE(e && dev_ws, "lg_engine_set_workspace: null argument");
+    LG_REQUIRE(((uintptr_t)dev_ws & 255) == 0, "workspace must be 256-byte aligned");
+    Workspace tmp;
+    const size_t needb = e->carve(tmp, (char*)dev_ws, rows, max_seq);
+    LG_REQUIRE(bytes >= needb, "workspace too small: %zu < %zu", bytes, needb);
+    tmp.base = (char*)dev_ws;
+    tmp.bytes = bytes;
+    e->ws = tmp;
+    return 0;
+}
+
+static int check_ready(lg_engine* e, int rows, int seq) {
+    LG_REQUIRE(e && e->finalized, "engine not finalized");
+    LG_REQUIRE(e->ws.base, "workspace not set");
+    LG_REQUIRE(rows <= e->ws.rows, "rows %d exceed workspace rows %d", rows, e->ws.rows);
+    LG_REQUIRE(seq <= e->ws.max_seq, "sequence %d exceeds workspace max_seq %d", seq, e->ws.max_seq);
+    LG_REQUIRE(seq <= e->cfg.cls_token_num + e->cfg.block_size, "sequence %d exceeds the RoPE table (%d)", seq,
+               e->cfg.cls_token_num + e->cfg.block_size);
+    return 0;
+}
+
+static int round_logits_inplace(float* logits, size_t n, cudaStream_t st);
+
+int lg_prefill(lg_engine* e, const void* cond, const float* emb_mask, int B, int T, int use_cfg, float* logits_out,
+               void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = use_cfg ? 2 * B : B;
+    LG_TRY(check_ready(e, R, T));
+    LG_REQUIRE(cond && logits_out && B > 0, "lg_prefill: bad argument");
+    LG_REQUIRE(T == e->cfg.cls_token_num, "lg_prefill: T=%d must equal cls_token_num=%d", T, e->cfg.cls_token_num);
+    LG_TRY(e->embed_cond(cond, B, R, T, st));
+    PosArg pos{nullptr, 0};
+    LG_TRY(e->forward(R * T, T, pos, emb_mask, B, logits_out, false, st));
+    if (e->cfg.dtype == LG_DTYPE_BF16) LG_TRY(round_logits_inplace(logits_out, (size_t)R * e->cfg.vocab_size, st));
+    return 0;
+}
+
+int lg_decode_step(lg_engine* e, const int32_t* tokens, int B, int pos, int use_cfg, float* logits_out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = use_cfg ? 2 * B : B;
+    LG_TRY(check_ready(e, R, pos + 1));
+    LG_REQUIRE(tokens && logits_out && B > 0 && pos >= 0, "lg_decode_step: bad argument");
+    LG_TRY(launch_embed(e->tok_emb, tokens, B, R, -1, e->cfg.dim, e->cfg.dtype, e->ws.h, st));
+    PosArg p{nullptr, pos};
+    LG_TRY(e->forward(R, 1, p, nullptr, B, logits_out, false, st));
+    if (e->cfg.dtype == LG_DTYPE_BF16) LG_TRY(round_logits_inplace(logits_out, (size_t)R * e->cfg.vocab_size, st));
+    return 0;
+}
+
+int lg_sample(const float* logits, int B, int V, int mix_cfg, int round_dtype, const lg_sample_cfg* sc, uint64_t step,
+              int32_t* out_idx, float* out_probs, void* stream) {
+    LG_REQUIRE(logits && sc && out_idx, "lg_sample: null argument");
+    SampleArgs a{};
+    a.logits = logits; a.B = B; a.V = V; a.mix_cfg = mix_cfg; a.round_bf16 = round_dtype == LG_DTYPE_BF16;
+    a.cfg_scale = sc->cfg_scale; a.cfg_interval = sc->cfg_interval; a.temperature = sc->temperature;
+    a.top_k = sc->top_k; a.top_p = sc->top_p; a.greedy = sc->greedy; a.seed = sc->seed; a.step = step;
+    a.out_idx = out_idx; a.out_probs = out_probs;
+    return launch_sample(a, (cudaStream_t)stream);
+}
+
+int lg_generate(lg_engine* e, const void* cond, const float* emb_mask, int B, int T, int S, const lg_sample_cfg* sc,
+                int32_t* out_tokens, float* dbg_logits, const int32_t* teacher, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LG_REQUIRE(cond && sc && out_tokens && B > 0 && S > 0, "lg_generate: bad argument");
+    const bool use_cfg = sc->cfg_scale > 1.0f;  // generate.py:128
+    const int R = use_cfg ? 2 * B : B;
+    LG_TRY(check_ready(e, R, T + S));
+    LG_REQUIRE(T == e->cfg.cls_token_num, "lg_generate: T=%d must equal cls_token_num=%d", T, e->cfg.cls_token_num);
+    if (emb_mask) LG_REQUIRE(e->cfg.model_type == LG_MODEL_T2I, "emb_masks only apply to t2i models");
+    Workspace& ws = e->ws;
+    int* d_pos = ws.counters;
+    int* d_step = ws.counters + 1;
+
+    SampleArgs sa{};
+    sa.logits = ws.logits; sa.B = B; sa.V = e->cfg.vocab_size; sa.mix_cfg = use_cfg;
+    sa.round_bf16 = e->cfg.dtype == LG_DTYPE_BF16;
+    sa.cfg_scale = sc->cfg_scale; sa.cfg_interval = sc->cfg_interval; sa.temperature = sc->temperature;
+    sa.top_k = sc->top_k; sa.top_p = sc->top_p; sa.greedy = sc->greedy; sa.seed = sc->seed;
+    sa.out_seq = out_tokens; sa.seq_stride = S; sa.next_tokens = ws.tokens; sa.teacher = teacher;
+    sa.dbg_logits = dbg_logits;
+
+    // ---- prefill (generate.py:167-169)
+    LG_TRY(e->embed_cond(cond, B, R, T, st));
+    LG_TRY(e->forward(R * T, T, PosArg{nullptr, 0}, emb_mask, B, ws.logits, false, st));
+    sa.step = 0; sa.step_dev = nullptr;
+    LG_TRY(launch_sample(sa, st));
+    if (S == 1) return 0;
+
+    // ---- decode loop (generate.py:105-123), device-resident counters
+    LG_TRY(launch_set_counters(d_pos, T, d_step, 1, st));
+    sa.step_dev = d_step;
+    auto body = [&]() -> int {
+        LG_TRY(launch_embed(e->tok_emb, ws.tokens, B, R, -1, e->cfg.dim, e->cfg.dtype, ws.h, st));
+        LG_TRY(e->forward(R, 1, PosArg{d_pos, 0}, emb_mask, B, ws.logits, false, st));
+        LG_TRY(launch_sample(sa, st));
+        LG_TRY(launch_advance(d_pos, d_step, st));
+        return 0;
+    };
+    LG_TRY(body());  // first decode step runs eagerly (also sets every kernel attribute outside capture)
+    const int remaining = S - 2;
+    if (remaining <= 0) return 0;
+    if (!e->use_graph || remaining < 3) {
+        for (int i = 0; i < remaining; ++i) LG_TRY(body());
+        return 0;
+    }
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    LG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    const uint64_t before = g_lg_launches.load();
+    const int rc = body();
+    const uint64_t per_step = g_lg_launches.load() - before;
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc < 0) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    LG_REQUIRE(ce == cudaSuccess && graph, "stream capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        return lg_fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    }
+    g_lg_launches.fetch_sub(per_step);  // the capture pass launched nothing
+    int ret = 0;
+    for (int i = 0; i < remaining; ++i) {
+        ce = cudaGraphLaunch(exec, st);
+        if (ce != cudaSuccess) { ret = lg_fail("cudaGraphLaunch failed: %s", cudaGetErrorString(ce)); break; }
+        g_lg_launches.fetch_add(per_step);
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    return ret;
+}
+
+int lg_test_gemm(const void* x, const void* w, int M, int N, int K, int dtype, float* y, void* dev_scratch,
+                 size_t scratch_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LG_REQUIRE(x && w && y && dev_scratch, "lg_test_gemm: null argument");
+    const size_t needf = gemm_partial_floats(M, N, K, dtype);
+    LG_REQUIRE(scratch_bytes >= needf * sizeof(float), "lg_test_gemm: scratch %zu < %zu", scratch_bytes, needf * sizeof(float));
+    GemmPlan plan;
+    LG_TRY(gemm_partial(x, K, w, nullptr, 0, M, N, K, dtype, (float*)dev_scratch, &plan, st));
+    return launch_reduce_f32((const float*)dev_scratch, plan.ksplit, M, N, y, st);
+}
+
+}  // extern "C"
+
+namespace {
+__global__ void round_bf16_kernel(float* p, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = round_bf16(p[i]);
+}
+}  // namespace
+static int round_logits_inplace(float* logits, size_t n, cudaStream_t st) {
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    round_bf16_kernel<<<blocks, 256, 0, st>>>(logits, n);
+    LG_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,100 @@
+// Internal launch API shared by the translation units of libllamagen_b200.so.
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// sampling.cu
+// ------------------------------------------------------------------------------------------------
+struct SampleArgs {
+    const float* logits;   // [rows, V], cond rows first
+    int B, V;
+    int mix_cfg;           // rows == 2B and CFG mixing requested
+    int round_bf16;        // round raw logits to bf16 before use (bf16 head output, gpt.py:368)
+    float cfg_scale;
+    int cfg_interval;
+    float temperature;
+    int top_k;
+    float top_p;
+    int greedy;
+    uint64_t seed;
+    uint64_t step;         // index of the token being produced (0 = prefill sample)
+    const int* step_dev;   // when non-null the step is read from device memory (graph replay)
+    int row_offset;        // added to the image index in the RNG stream (multi-rank decorrelation)
+    int32_t* out_idx;      // [B] or null
+    float* out_probs;      // [B, V] or null
+    int32_t* out_seq;      // [B, seq_stride] or null: out_seq[b, step] = idx
+    int seq_stride;
+    int32_t* next_tokens;  // [B] or null: token fed to the next decode step
+    const int32_t* teacher;// [B, seq_stride] or null: teacher-forced next token
+    float* dbg_logits;     // [S, B, V] or null: mixed logits before temperature
+};
+int launch_sample(const SampleArgs& a, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// gemm.cu — y_partial[ks][M][N] (f32) = x[M,K] * W[N,K]^T ; W may be two row segments (w1 | w3).
+// ------------------------------------------------------------------------------------------------
+struct GemmPlan {
+    int ksplit;            // number of fp32 partial slabs written
+};
+// Returns the plan used; partial must hold ksplit_max(M,N,K) * M * N floats (see gemm_partial_floats).
+size_t gemm_partial_floats(int M, int N, int K, int dtype);
+int gemm_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
+                 int dtype, float* partial, GemmPlan* plan, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// xf_kernels.cu — transformer glue kernels (all templated on the activation dtype internally)
+// ------------------------------------------------------------------------------------------------
+struct PosArg {            // position of row-block: pos = (dev ? *dev : value) + t
+    const int* dev;
+    int value;
+};
+
+// out[r,:] = table[idx(r),:]; idx(r) = r < B ? src[r] : (null_idx >= 0 ? null_idx : src[r-B])
+int launch_embed(const void* table, const int32_t* src, int B, int R, int null_idx, int D, int dtype,
+                 void* out, cudaStream_t st);
+// t2i cond rows: out[(r*T+t),:] = r < B ? cond[r,t,:] : uncond[t,:]   (generate.py:137)
+int launch_build_caption_rows(const void* cond, const void* uncond, int B, int R, int T, int C, int dtype,
+                              void* out, cudaStream_t st);
+// xn = rmsnorm(x) * w   (gpt.py:143-148)
+int launch_rmsnorm(const void* x, const void* w, void* xn, int M, int D, float eps, int dtype, cudaStream_t st);
+
+struct QkvEpiArgs {
+    const float* partial; int ksplit;   // [ks][M][3D]
+    int M, Tq, D, H, hd;
+    PosArg pos;
+    const float* freqs;                 // [P, hd/2, 2]
+    void* q;                            // [M, D]
+    void* kcache; void* vcache;         // [R, H, maxS, hd] for this layer
+    int maxS;
+    int dtype;
+};
+int launch_qkv_epilogue(const QkvEpiArgs& a, cudaStream_t st);
+
+// h += T(sum partial); optionally xn = rmsnorm(h) * norm_w  (fused residual + next norm)
+int launch_residual_norm(const float* partial, int ksplit, int M, int D, void* h, const void* norm_w, void* xn,
+                         float eps, int dtype, cudaStream_t st);
+// out[m, j] = silu(T(p[m, j])) * T(p[m, F + j])   (gpt.py:167)
+int launch_silu_mul(const float* partial, int ksplit, int M, int F, void* out, int dtype, cudaStream_t st);
+// out = gelu_tanh(T(p))  (gpt.py:122-131)   /   out = T(p)
+int launch_store_act(const float* partial, int ksplit, int M, int N, void* out, int gelu, int dtype, cudaStream_t st);
+// logits f32 [R, V] = sum partial rows (only needed when ksplit > 1 or rows are strided)
+int launch_reduce_f32(const float* partial, int ksplit, int M, int N, float* out, cudaStream_t st);
+// gather last-position rows: out[r,:] = in[(r*T + T-1),:]
+int launch_gather_last(const void* in, int R, int T, int D, int dtype, void* out, cudaStream_t st);
+
+struct AttnArgs {
+    const void* q;          // [M, D] post-RoPE
+    const void* kcache; const void* vcache;   // [R, H, maxS, hd]
+    void* out;              // [M, D]
+    int R, Tq, H, hd, maxS;
+    PosArg pos;             // query t attends keys [0, pos+t]
+    const float* emb_mask;  // [B, Tc] or null  (generate.py:154-163)
+    int B, Tc;
+    float scale;
+    int dtype;
+};
+int launch_attention(const AttnArgs& a, cudaStream_t st);
+
+// *pos += 1; *step += 1  (device-side loop counters for graph replay)
+int launch_advance(int* pos, int* step, cudaStream_t st);
+int launch_set_counters(int* pos, int pos_v, int* step, int step_v, cudaStream_t st);

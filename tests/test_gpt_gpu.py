@@ -1,0 +1,151 @@
+"""GPU parity of the AR engine (lg_generate / lg_prefill / lg_decode_step) against the oracle and the
+reference-produced golden vectors.
+
+Protocol: fp32 "exact" mode must reproduce the fp32 oracle's greedy token ids bit-exactly and
+its logits to 1e-4; bf16 mode is checked teacher-forced at every step against the fp32 oracle run on the
+same bf16-rounded weights (tolerance 4e-2 at logit scale ~2.7 = the oracle's own bf16-vs-fp32 spread) with
+arg-max agreement wherever the oracle's top-1/top-2 gap exceeds twice the tolerance."""
+import pytest
+import torch
+
+from oracle import GPTOracle
+from util import build_gpt, cpu_state, load_golden, oracle_cfg, top2_gap
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 4e-2
+
+
+def _gen(model, cond, S, em, **kw):
+    from llamagen_b200 import generate
+    toks, logits = generate(model, cond.cuda(), S, emb_masks=None if em is None else em.cuda(), sample_logits=False,
+                            return_logits=True, **kw)
+    torch.cuda.synchronize()
+    return toks.cpu(), logits.cpu()
+
+
+@pytest.mark.parametrize("name", ["gpt_c2i.pt", "gpt_t2i.pt"])
+@pytest.mark.parametrize("cfg_scale", [1.0, 4.0])
+def test_fp32_matches_reference_golden(name, cfg_scale):
+    g = load_golden(name)
+    m = build_gpt(g["cfg"], g["state_dict"], torch.float32)
+    toks, logits = _gen(m, g["cond"], g["S"], g["emb_masks"], cfg_scale=cfg_scale)
+    ref_l = g[f"logits_cfg{cfg_scale}"]
+    assert (logits - ref_l).abs().max().item() <= FP32_TOL
+    assert torch.equal(toks, g[f"tokens_cfg{cfg_scale}"]), "greedy token ids must be bit-exact in fp32 mode"
+
+
+@pytest.mark.parametrize("name", ["gpt_c2i.pt", "gpt_t2i.pt"])
+def test_fp32_cfg_interval_golden(name):
+    g = load_golden(name)
+    m = build_gpt(g["cfg"], g["state_dict"], torch.float32)
+    toks, _ = _gen(m, g["cond"], g["S"], g["emb_masks"], cfg_scale=4.0, cfg_interval=3)
+    assert torch.equal(toks, g["tokens_cfg4.0_int3"])
+
+
+@pytest.mark.parametrize("name", ["gpt_c2i.pt", "gpt_t2i.pt"])
+def test_graph_replay_equals_eager(name, monkeypatch):
+    g = load_golden(name)
+    m = build_gpt(g["cfg"], g["state_dict"], torch.float32)
+    t_graph, l_graph = _gen(m, g["cond"], g["S"], g["emb_masks"], cfg_scale=4.0)
+    monkeypatch.setenv("LG_NO_GRAPH", "1")
+    m2 = build_gpt(g["cfg"], g["state_dict"], torch.float32)
+    t_eager, l_eager = _gen(m2, g["cond"], g["S"], g["emb_masks"], cfg_scale=4.0)
+    assert torch.equal(t_graph, t_eager) and torch.equal(l_graph, l_eager)
+
+
+@pytest.mark.parametrize("name", ["gpt_c2i.pt", "gpt_t2i.pt"])
+def test_bf16_teacher_forced_vs_oracle(name):
+    g = load_golden(name)
+    m = build_gpt(g["cfg"], g["state_dict"], torch.bfloat16)
+    sd = cpu_state(m)                                   # bf16 weights
+    cond = g["cond"] if name == "gpt_c2i.pt" else g["cond"].bfloat16()
+    orc = GPTOracle(sd, g["cfg"])                       # bf16 oracle: same dtype, same rounding points
+    ref_t, ref_l = orc.generate(cond, g["S"], emb_masks=g["emb_masks"], cfg_scale=4.0, sample_logits=False)
+    toks, logits = _gen(m, cond, g["S"], g["emb_masks"], cfg_scale=4.0, teacher=ref_t[:, :].clone())
+    assert (logits - ref_l).abs().max().item() <= BF16_TOL
+    decisive = top2_gap(ref_l) > 2 * BF16_TOL
+    assert torch.equal(logits.argmax(-1)[decisive], ref_l.argmax(-1)[decisive])
+    assert torch.equal(toks.t()[decisive], ref_t.t()[decisive])
+
+
+def _registry_model(name, dtype, seed, **kw):
+    from llamagen_b200 import GPT_models
+    torch.manual_seed(seed)
+    m = GPT_models[name](**kw)
+    m.output.weight.data.normal_(std=0.02)
+    return m.to(device="cuda", dtype=dtype).eval()
+
+
+def test_gpt_b_fp32_greedy_bit_exact_vs_oracle():
+    """BASELINE config C1 shape (GPT-B c2i 16x16, cfg 4.0) in the fp32 exact mode, truncated to 24 tokens."""
+    m = _registry_model("GPT-B", torch.float32, 0, block_size=256, vocab_size=16384)
+    cond = torch.tensor([207, 360])
+    S = 24
+    orc = GPTOracle(cpu_state(m), oracle_cfg(m))
+    ref_t, ref_l = orc.generate(cond, S, cfg_scale=4.0, sample_logits=False)
+    toks, logits = _gen(m, cond, S, None, cfg_scale=4.0)
+    assert (logits - ref_l).abs().max().item() <= FP32_TOL
+    assert torch.equal(toks, ref_t)
+
+
+@pytest.mark.parametrize("B", [1, 9, 40])
+def test_gpt_l_bf16_teacher_forced(B):
+    """GPT-L bf16 (BASELINE config C2 model): B=1 exercises the skinny CUDA-core GEMM (R=2), B=9 / 40 the
+    tensor-core path with BM=32 / 128 tiles. Reference = fp32 oracle on the same bf16-rounded weights."""
+    m = _registry_model("GPT-L", torch.bfloat16, 1, block_size=256, vocab_size=16384)
+    torch.manual_seed(B)
+    cond = torch.randint(0, 1000, (B,))
+    S = 6
+    orc = GPTOracle(cpu_state(m, torch.float32), oracle_cfg(m))
+    ref_t, ref_l = orc.generate(cond, S, cfg_scale=4.0, sample_logits=False)
+    toks, logits = _gen(m, cond, S, None, cfg_scale=4.0, teacher=ref_t.clone())
+    assert (logits - ref_l).abs().max().item() <= BF16_TOL
+    decisive = top2_gap(ref_l) > 2 * BF16_TOL
+    assert torch.equal(logits.argmax(-1)[decisive], ref_l.argmax(-1)[decisive])
+
+
+def test_gpt_3b_head_dim_100_bf16():
+    """GPT-3B has head_dim 100 (not a multiple of 16). 4 layers of the 3B shape keep the CPU oracle fast."""
+    from llamagen_b200.gpt import ModelArgs, Transformer
+    torch.manual_seed(3)
+    m = Transformer(ModelArgs(n_layer=4, n_head=32, dim=3200, block_size=576, vocab_size=16384))
+    m.output.weight.data.normal_(std=0.02)
+    m = m.to(device="cuda", dtype=torch.bfloat16).eval()
+    cond = torch.tensor([1, 2, 3])
+    S = 5
+    orc = GPTOracle(cpu_state(m, torch.float32), oracle_cfg(m))
+    ref_t, ref_l = orc.generate(cond, S, cfg_scale=4.0, sample_logits=False)
+    toks, logits = _gen(m, cond, S, None, cfg_scale=4.0, teacher=ref_t.clone())
+    assert (logits - ref_l).abs().max().item() <= BF16_TOL
+
+
+def test_forward_api_matches_generate_path():
+    """Transformer.forward (prefill / decode, gpt.py:348-368 semantics) is usable by the reference's own Python loop."""
+    g = load_golden("gpt_c2i.pt")
+    m = build_gpt(g["cfg"], g["state_dict"], torch.float32)
+    cond = g["cond"].cuda()
+    B = cond.shape[0]
+    cond2 = torch.cat([cond, torch.full_like(cond, m.num_classes)])
+    m.setup_caches(2 * B, 1 + g["S"], torch.float32)
+    logits, _ = m(None, cond2, torch.arange(0, 1, device="cuda"))
+    mixed = logits[B:, -1] + (logits[:B, -1] - logits[B:, -1]) * 4.0
+    ref = g["logits_cfg4.0"][0]
+    assert (mixed.cpu() - ref).abs().max().item() <= FP32_TOL
+    tok = mixed.argmax(-1, keepdim=True)
+    logits, _ = m(torch.cat([tok, tok]), None, torch.tensor([1], device="cuda", dtype=torch.int))
+    mixed = logits[B:, -1] + (logits[:B, -1] - logits[B:, -1]) * 4.0
+    assert (mixed.cpu() - g["logits_cfg4.0"][1]).abs().max().item() <= FP32_TOL
+
+
+def test_sampling_run_is_seed_reproducible_and_in_range():
+    from llamagen_b200 import generate
+    m = _registry_model("GPT-B", torch.bfloat16, 5, block_size=256, vocab_size=16384)
+    cond = torch.randint(0, 1000, (4,), device="cuda")
+    a = generate(m, cond, 32, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, sample_logits=True, seed=11)
+    b = generate(m, cond, 32, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, sample_logits=True, seed=11)
+    c = generate(m, cond, 32, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, sample_logits=True, seed=12)
+    assert a.dtype == torch.int32 and tuple(a.shape) == (4, 32)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert int(a.min()) >= 0 and int(a.max()) < 16384

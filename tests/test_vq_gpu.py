@@ -1,0 +1,91 @@
+"""GPU parity of the VQ decode path (lg_vq_decode) and the codebook argmin (lg_vq_argmin).
+
+Tolerance (stated): the sm_100a decoder feeds bf16 operands to the tensor cores with fp32
+accumulation and keeps activations in bf16; the oracle's own bf16-vs-fp32 spread on this decoder is
+max-abs 0.146 / mean-abs 0.010 at output std 0.39, so we require max-abs <= 0.2 and mean-abs <= 0.02
+against the fp32 oracle, and <= 1 LSB mean error after the uint8 conversion of sample_c2i_ddp.py:143."""
+import pytest
+import torch
+
+from oracle import VQOracle
+from util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_pixels(out, ref):
+    scale = max(1.0, ref.std().item() / 0.39)
+    err = (out - ref).abs()
+    assert err.max().item() <= 0.2 * scale, err.max().item()
+    assert err.mean().item() <= 0.02 * scale, err.mean().item()
+    u8 = lambda x: torch.clamp(127.5 * x + 128.0, 0, 255).to(torch.uint8).float()
+    assert (u8(out) - u8(ref)).abs().mean().item() <= 1.0 * scale
+
+
+def _tiny_model(g):
+    from llamagen_b200.vq_model import ModelArgs, VQModel
+    m = VQModel(ModelArgs(codebook_size=64, codebook_embed_dim=8, encoder_ch_mult=g["ch_mult"], decoder_ch_mult=g["ch_mult"],
+                          z_channels=g["z_channels"]), ch=g["ch"])
+    missing, unexpected = m.load_state_dict(g["state_dict"], strict=False)
+    assert not unexpected and all(k.startswith(("encoder.", "quant_conv.", "quantize.codebook_used")) for k in missing)
+    return m.cuda().eval()
+
+
+def test_tiny_decoder_matches_reference_golden():
+    g = load_golden("vq_tiny.pt")
+    m = _tiny_model(g)
+    out = m.decode_code(g["codes"].cuda(), [2, 8, 4, 4]).cpu()
+    assert tuple(out.shape) == tuple(g["pixels"].shape)
+    _check_pixels(out, g["pixels"])
+
+
+def test_tiny_argmin_matches_reference_golden():
+    g = load_golden("vq_tiny.pt")
+    m = _tiny_model(g)
+    idx = m.quantize_indices(g["z"].cuda()).cpu()
+    assert torch.equal(idx, g["argmin"])
+
+
+@pytest.mark.parametrize("name,g,B", [("VQ-16", 16, 3), ("VQ-16", 24, 1), ("VQ-8", 16, 2)])
+def test_full_decoder_vs_oracle(name, g, B):
+    from llamagen_b200 import VQ_models
+    torch.manual_seed(g + B)
+    m = VQ_models[name](codebook_size=16384, codebook_embed_dim=8).cuda().eval()
+    codes = torch.randint(0, 16384, (B, g * g))
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    ref = VQOracle(sd, ch_mult=m.config.decoder_ch_mult).decode_code(codes, [B, 8, g, g])
+    out = m.decode_code(codes.cuda(), [B, 8, g, g]).cpu()
+    assert tuple(out.shape) == tuple(ref.shape)
+    _check_pixels(out, ref)
+
+
+def test_decode_is_batch_invariant():
+    """Images are independent (replica sharding relies on it): decoding a batch == decoding its halves."""
+    from llamagen_b200 import VQ_models
+    torch.manual_seed(0)
+    m = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).cuda().eval()
+    codes = torch.randint(0, 16384, (4, 256), device="cuda")
+    full = m.decode_code(codes, [4, 8, 16, 16])
+    a = m.decode_code(codes[:2], [2, 8, 16, 16])
+    b = m.decode_code(codes[2:], [2, 8, 16, 16])
+    assert torch.equal(full, torch.cat([a, b]))
+
+
+def test_argmin_full_codebook_vs_oracle():
+    from llamagen_b200 import VQ_models
+    torch.manual_seed(1)
+    m = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).cuda().eval()
+    m.quantize.embedding.weight.data.copy_(torch.nn.functional.normalize(torch.randn(16384, 8), dim=-1))
+    z = torch.randn(4, 8, 16, 16)
+    orc = VQOracle({k: v.cpu() for k, v in m.state_dict().items()}, ch_mult=m.config.decoder_ch_mult)
+    ref = orc.argmin_indices(z)
+    idx = m.quantize_indices(z.cuda()).cpu()
+    if not torch.equal(idx, ref):
+        # a mismatch is only acceptable on an fp32 near-tie of the two distances
+        e = torch.nn.functional.normalize(m.quantize.embedding.weight.data.cpu(), dim=-1)
+        zf = torch.nn.functional.normalize(z.permute(0, 2, 3, 1).reshape(-1, 8), dim=-1)
+        bad = (idx != ref).nonzero().view(-1)
+        assert bad.numel() <= 4
+        d = ((zf[bad, None, :] - e[None, :, :]) ** 2).sum(-1)
+        gap = (d.gather(1, idx[bad, None]) - d.gather(1, ref[bad, None])).abs().max().item()
+        assert gap <= 1e-6, gap
