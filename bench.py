@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — images/sec end-to-end (c2i, 16x16 tokens) on N B200s, plus roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): LlamaGen-L c2i 256px (16x16 = 256 tokens), cfg_scale 4.0, top_k 2000,
+temperature 1.0, bf16 GPT + VQ-16 decode, batch 64 per GPU, random-init weights (non-zero head),
+synthetic class labels.  One "step" = generate() + decode_code() for one batch of 64 images.
+Scaling is weak: every rank samples its own 64 images per step (replica data-parallel); NCCL is used
+only for the initial weight broadcast and the barriers.
+
+Prints ONE JSON line (see the task contract): value = whole-job images/s with labels resident in HBM;
+e2e = same through the public API with pinned-host labels (H2D) and uint8 pixels copied back (D2H) every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec end-to-end (c2i, 16x16 tokens)"
+UNIT = "images/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    p.add_argument("--gpt-model", default="GPT-L")
+    p.add_argument("--image-size", type=int, default=256)
+    p.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    p.add_argument("--cfg-scale", type=float, default=4.0)
+    p.add_argument("--top-k", type=int, default=2000)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-roofline", action="store_true")
+    p.add_argument("--seed", type=int, default=0)
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- model shapes
+def model_dims(name):
+    from llamagen_b200.gpt import _SHAPES, ModelArgs
+    L, H, D = _SHAPES[name]
+    F = ModelArgs(n_layer=L, n_head=H, dim=D).ffn_dim
+    return L, H, D, F
+
+
+def algorithmic(name, R, S, T=1, V=16384):
+    """algorithmic bytes / flops of one decode step averaged over the S steps (bf16)."""
+    L, H, D, F = model_dims(name)
+    cbar = T + (S - 1) / 2.0
+    w_bytes = 2 * (L * (4 * D * D + 3 * D * F) + D * V)
+    kv_read = 4 * L * R * D * cbar
+    kv_write = 4 * L * R * D
+    step_bytes = w_bytes + kv_read + kv_write + 4 * R * V
+    step_flops = 2 * R * (L * (4 * D * D + 3 * D * F) + D * V) + 4 * L * R * D * cbar
+    per_launch = {   # bytes one launch of each kernel class must move (weights + activations in/out)
+        "attention": 4 * R * D * cbar + 4 * R * D,
+        "gemm_qkv": 2 * 3 * D * D + 2 * R * D + 4 * R * 3 * D,
+        "gemm_wo": 2 * D * D + 2 * R * D + 4 * R * D,
+        "gemm_w13": 2 * 2 * F * D + 2 * R * D + 4 * R * 2 * F,
+        "gemm_w2": 2 * D * F + 2 * R * F + 4 * R * D,
+        "gemm_head": 2 * V * D + 2 * R * D + 4 * R * V,
+    }
+    per_launch_flops = {"gemm_qkv": 2 * R * 3 * D * D, "gemm_wo": 2 * R * D * D, "gemm_w13": 2 * R * 2 * F * D,
+                        "gemm_w2": 2 * R * D * F, "gemm_head": 2 * R * V * D, "attention": 4 * R * D * cbar}
+    return dict(step_bytes=step_bytes, step_flops=step_flops, per_launch=per_launch, per_launch_flops=per_launch_flops)
+
+
+VQ_GFLOP_PER_IMAGE = {16: 252.7, 24: 570.1, 32: 1017.3}   # SURVEY §8a-7 (conv-hook count on the reference)
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    """The reference's algorithm on the host cores: oracle port (the reference is Python and cannot travel to the
+    GPU box), torch CPU fp32, all host threads. Each step = a BOUNDED sample of the workload: prefill + 3 decode steps
+    at the full batch (the reference attends over all max_seq slots every step, so per-step cost is constant) + VQ
+    decode of 1 image, extrapolated to 256 steps / `batch` images."""
+    import torch
+    from llamagen_b200 import GPT_models, VQ_models
+    from oracle import GPTOracle, VQOracle
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(args.seed)
+    g = args.image_size // 16
+    S = g * g
+    gpt = GPT_models[args.gpt_model](block_size=S, vocab_size=16384)
+    gpt.output.weight.data.normal_(std=0.02)
+    c = gpt.config
+    cfg = dict(n_layer=c.n_layer, n_head=c.n_head, dim=c.dim, norm_eps=c.norm_eps, rope_base=c.rope_base, num_classes=c.num_classes,
+               cls_token_num=1, block_size=S, model_type="c2i")
+    orc = GPTOracle(gpt.state_dict(), cfg)
+    vq = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8)
+    vorc = VQOracle(vq.state_dict())
+    B = args.batch
+    n_dec = 3
+    cond = torch.randint(0, 1000, (B,))
+
+    def one_sample():
+        # generate() on the oracle, truncated to 1 + n_dec tokens but with the full-length cache (max_seq = 1 + S)
+        t0 = time.perf_counter()
+        orc.setup(2 * B, 1 + S)
+        cond_all = torch.cat([cond, torch.full_like(cond, c.num_classes)])
+        orc.math_sdp = False
+        logits = orc.forward(None, cond_all, torch.arange(0, 1))
+        from oracle import cfg_mix_oracle, sample_oracle
+        nxt = sample_oracle(cfg_mix_oracle(logits, args.cfg_scale)[:, -1], top_k=args.top_k)[0]
+        t_prefill = time.perf_counter() - t0
+        orc.math_sdp = True
+        t1 = time.perf_counter()
+        pos = torch.tensor([1], dtype=torch.int)
+        for _ in range(n_dec):
+            logits = orc.forward(torch.cat([nxt, nxt]).view(-1, 1), None, pos)
+            nxt = sample_oracle(cfg_mix_oracle(logits, args.cfg_scale)[:, -1], top_k=args.top_k)[0]
+            pos += 1
+        t_dec = (time.perf_counter() - t1) / n_dec
+        t2 = time.perf_counter()
+        vorc.decode_code(torch.randint(0, 16384, (1, S)), [1, 8, g, g])
+        t_vq = time.perf_counter() - t2
+        total = t_prefill + (S - 1) * t_dec + B * t_vq
+        return B / total, dict(prefill_s=t_prefill, decode_step_s=t_dec, vq_image_s=t_vq)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            one_sample()
+        vals, detail = [], None
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            v, detail = one_sample()
+            vals.append(v)
+        wall = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    sample = f"prefill + {n_dec} decode steps at B={B} (R={2*B}) + VQ decode of 1 image per step, extrapolated to {S} tokens x {B} images"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"LlamaGen {args.gpt_model} c2i {args.image_size}px ({g}x{g} tokens), cfg={args.cfg_scale}, top_k={args.top_k}, batch={B}, "
+                                   "oracle port of the reference on host CPU (fp32, torch)", "extrapolated": True},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "detail": detail},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from llamagen_b200 import GPT_models, VQ_models, generate, _lib
+    from llamagen_b200 import distributed as lgd
+
+    rank, world, local = lgd.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    g = args.image_size // 16
+    S = g * g
+    B = args.batch
+    R = 2 * B if args.cfg_scale > 1.0 else B
+
+    # weights: rank 0 initialises, NCCL broadcasts once (north_star: "NCCL only for the initial weight broadcast")
+    torch.manual_seed(args.seed)
+    gpt = GPT_models[args.gpt_model](block_size=S, vocab_size=16384)
+    gpt.output.weight.data.normal_(std=0.02)
+    gpt = gpt.to(device=dev, dtype=torch.bfloat16).eval()
+    vq = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).to(dev).eval()
+    bcast_bytes = lgd.broadcast_module(gpt) + lgd.broadcast_module(vq)
+    torch.manual_seed(lgd.rank_seed(args.seed, rank, world))
+    qz = [B, 8, g, g]
+    kw = dict(cfg_scale=args.cfg_scale, cfg_interval=-1, temperature=1.0, top_k=args.top_k, top_p=1.0, sample_logits=True)
+
+    def step_resident(labels_dev):
+        toks = generate(gpt, labels_dev, S, **kw)
+        return vq.decode_code(toks, qz)
+
+    host_labels = torch.randint(0, 1000, (B,), dtype=torch.int64).pin_memory()
+    host_pixels = torch.empty(B, args.image_size, args.image_size, 3, dtype=torch.uint8).pin_memory()
+
+    def step_e2e():
+        labels = host_labels.to(dev, non_blocking=True)                       # H2D every step
+        img = step_resident(labels)
+        u8 = torch.clamp(127.5 * img + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)   # sample_c2i_ddp.py:143
+        host_pixels.copy_(u8, non_blocking=True)                              # D2H every step
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    labels_dev = torch.randint(0, 1000, (B,), device=dev)
+    for _ in range(max(args.warmup, 3)):
+        step_resident(labels_dev)
+    step_e2e()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.lg_reset_launch_count()
+    ms = timed(lambda: step_resident(labels_dev), args.steps)
+    launches = int(lib.lg_launch_count())
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1000.0)
+    e2e_value = world * B * args.steps / (ms_e2e / 1000.0)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"LlamaGen {args.gpt_model} c2i {args.image_size}px ({g}x{g} tokens), cfg={args.cfg_scale}, top_k={args.top_k}, "
+                                   f"batch={B} per GPU (R={R} rows), AR sampling + VQ-16 decode to fp32 pixels",
+                       "global_batch": world * B, "parallelism": f"replica-dp{world}", "weights": "random-init, output head normal(0.02)",
+                       "l2": "working set per step (0.65 GB weights + KV cache up to 3.3 GB + 1 GB activations) exceeds the 126 MB L2; no flush needed",
+                       "weight_broadcast_bytes": bcast_bytes},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_labels.numel() * 8),
+                    "d2h_bytes_per_step": int(host_pixels.numel()), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks}
+
+    # ---------------- roofline leg: per-kernel-class CUDA-event timing of one extra (untimed) step, rank 0 only
+    if rank == 0 and not args.no_roofline:
+        pk = peaks()
+        lib.lg_profile_reset()
+        lib.lg_profile_enable(1)
+        step_resident(labels_dev)
+        torch.cuda.synchronize()
+        lib.lg_profile_enable(0)
+        classes, i = {}, 0
+        while True:
+            nm = lib.lg_profile_class_name(i)
+            if nm is None:
+                break
+            t, n = ctypes.c_double(), ctypes.c_uint64()
+            lib.lg_profile_read(i, ctypes.byref(t), ctypes.byref(n))
+            if n.value:
+                classes[nm.decode()] = {"total_ms": t.value, "launches": int(n.value), "avg_us": 1000.0 * t.value / n.value}
+            i += 1
+        alg = algorithmic(args.gpt_model, R, S)
+        dom = max((k for k in classes if k in alg["per_launch"]), key=lambda k: classes[k]["total_ms"], default=None)
+        if dom:
+            avg_s = classes[dom]["avg_us"] * 1e-6
+            ach = alg["per_launch"][dom] / avg_s / 1e9
+            line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                                "algorithmic_bytes_per_launch": alg["per_launch"][dom], "avg_launch_us": classes[dom]["avg_us"]}
+        total_ar = sum(v["total_ms"] for k, v in classes.items() if not k.startswith("vq_"))
+        total_vq = sum(v["total_ms"] for k, v in classes.items() if k.startswith("vq_"))
+        step_roof_ms = 1000.0 * max(alg["step_bytes"] / (pk["hbm_gbs"] * 1e9), alg["step_flops"] / (pk["bf16_sustained"] * 1e12))
+        vq_roof_ms = B * VQ_GFLOP_PER_IMAGE.get(g, 0.0) / (pk["bf16_sustained"] * 1e3) * 1e3
+        line["kernels"] = {k: {"avg_us": round(v["avg_us"], 2), "launches": v["launches"], "share": round(v["total_ms"] / (total_ar + total_vq), 4)}
+                           for k, v in classes.items()}
+        for k in classes:
+            if k in alg["per_launch"]:
+                s = classes[k]["avg_us"] * 1e-6
+                line["kernels"][k]["hbm_gbs"] = round(alg["per_launch"][k] / s / 1e9, 1)
+                line["kernels"][k]["tflops"] = round(alg["per_launch_flops"][k] / s / 1e12, 1)
+        if "vq_conv_gemm" in classes:
+            line["kernels"]["vq_conv_gemm"]["tflops"] = round(B * VQ_GFLOP_PER_IMAGE.get(g, 0.0) / classes["vq_conv_gemm"]["total_ms"], 1)
+        line["step_roofline"] = {"decode_step_floor_us": round(step_roof_ms * 1000, 1), "ar_floor_ms": round(step_roof_ms * S, 2),
+                                 "vq_floor_ms": round(vq_roof_ms, 2), "measured_ms_per_step": round(ms / args.steps, 2),
+                                 "frac_of_floor": round((step_roof_ms * S + vq_roof_ms) / (ms / args.steps), 4),
+                                 "profiled_ar_ms": round(total_ar, 2), "profiled_vq_ms": round(total_vq, 2)}
+
+    # ---------------- CPU baseline leg (rank 0, N=1 only): bounded sample of the same workload on the host cores
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                            "--gpt-model", args.gpt_model, "--image-size", str(args.image_size), "--batch", str(B)],
+                           capture_output=True, text=True, timeout=1500, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+        try:
+            ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        except Exception as ex:   # never silently drop the leg
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {ex}: {r.stderr[-300:]}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        run_reference(args, rank)
+        return
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -135,6 +135,15 @@ int  lg_vq_decode(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws,
 /* VectorQuantizer.forward index path (vq_model.py:215-233): z dev f32 NCHW [B, e_dim, g, g] -> idx int64 [B*g*g]. */
 int  lg_vq_argmin(lg_vq* v, const float* z_nchw, int B, int grid, int64_t* out_idx, void* stream);
 
+/* ---- per-kernel-class device timing for bench.py's roofline leg --------------------------------------
+ * While enabled, launches are bracketed by CUDA events on the launching stream (CUDA-graph replay is bypassed).
+ * lg_profile_read synchronises the device and returns the summed duration / launch count of one class
+ * (class ids: see `lg_profile_class_name`). */
+int         lg_profile_enable(int on);
+int         lg_profile_reset(void);
+int         lg_profile_read(int cls, double* total_ms, uint64_t* launches);
+const char* lg_profile_class_name(int cls);   /* NULL past the last class */
+
 /* ---- stand-alone kernels exported for unit parity tests ------------------------------------------- */
 /* y[M,N] (f32) = x[M,K] * w[N,K]^T, operands in `dtype`; the same dispatch the engine uses. */
 int  lg_test_gemm(const void* x, const void* w, int M, int N, int K, int dtype, float* y,

@@ -26,6 +26,8 @@ extern std::atomic<uint64_t> g_lg_launches;
                            cudaGetErrorString(_e));                                              \
     } while (0)
 
+// LG_DEBUG_SYNC=1 synchronises after every launch and logs the launch site (hang / fault localisation).
+bool lg_debug_sync();
 #define LG_LAUNCH_CHECK()                                                                        \
     do {                                                                                         \
         g_lg_launches.fetch_add(1, std::memory_order_relaxed);                                   \
@@ -33,6 +35,16 @@ extern std::atomic<uint64_t> g_lg_launches;
         if (_e != cudaSuccess)                                                                   \
             return lg_fail("%s:%d kernel launch failed: %s", __FILE__, __LINE__,                 \
                            cudaGetErrorString(_e));                                              \
+        if (lg_debug_sync()) {                                                                   \
+            fprintf(stderr, "[lg] launched %s:%d ...", __FILE__, __LINE__);                      \
+            fflush(stderr);                                                                      \
+            _e = cudaDeviceSynchronize();                                                        \
+            fprintf(stderr, " %s\n", cudaGetErrorString(_e));                                    \
+            fflush(stderr);                                                                      \
+            if (_e != cudaSuccess)                                                               \
+                return lg_fail("%s:%d kernel failed: %s", __FILE__, __LINE__,                    \
+                               cudaGetErrorString(_e));                                          \
+        }                                                                                        \
     } while (0)
 
 #define LG_TRY(expr)                                                                             \

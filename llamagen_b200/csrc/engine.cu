@@ -28,6 +28,60 @@ int lg_fail(const char* fmt, ...) {
     return -1;
 }
 std::atomic<uint64_t> g_lg_launches{0};
+bool lg_debug_sync() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LG_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// event-pair profiler
+namespace {
+struct ProfState {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;      // flat pairs
+    std::vector<int> cls;               // class of each recorded pair
+    size_t used = 0;                    // pairs recorded since the last drain
+    double total_ms[PC_COUNT] = {0};
+    uint64_t count[PC_COUNT] = {0};
+    int cur = -1;
+};
+ProfState g_prof;
+void prof_drain() {
+    if (g_prof.used == 0) return;
+    cudaDeviceSynchronize();
+    for (size_t i = 0; i < g_prof.used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]) == cudaSuccess) {
+            g_prof.total_ms[g_prof.cls[i]] += ms;
+            g_prof.count[g_prof.cls[i]] += 1;
+        }
+    }
+    g_prof.used = 0;
+}
+}  // namespace
+bool prof_enabled() { return g_prof.on; }
+void prof_begin(int cls, cudaStream_t st) {
+    if (!g_prof.on) return;
+    if (g_prof.used >= 16384) prof_drain();
+    if (g_prof.pool.size() < 2 * (g_prof.used + 1)) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        g_prof.pool.push_back(a);
+        g_prof.pool.push_back(b);
+        g_prof.cls.push_back(cls);
+    }
+    g_prof.cls[g_prof.used] = cls;
+    g_prof.cur = (int)g_prof.used;
+    cudaEventRecord(g_prof.pool[2 * g_prof.used], st);
+}
+void prof_end(cudaStream_t st) {
+    if (!g_prof.on || g_prof.cur < 0) return;
+    cudaEventRecord(g_prof.pool[2 * g_prof.cur + 1], st);
+    g_prof.used += 1;
+    g_prof.cur = -1;
+}
 
 namespace {
 
@@ -72,6 +126,13 @@ struct lg_engine {
     bool finalized = false;
     Workspace ws;
     bool use_graph = true;
+    cudaStream_t work = nullptr;          // engine-owned stream the generate loop (and its graph) runs on
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    ~lg_engine() {
+        if (work) cudaStreamDestroy(work);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+    }
 
     size_t carve(Workspace& o, char* base, int rows, int max_seq) const;
     int forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, float* logits_out, bool round_out,
@@ -137,28 +198,28 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
     const int R = M / Tq;
     const int dt = cfg.dtype;
     int ks = 1;
-    LG_TRY(launch_rmsnorm(ws.h, layers[0].attn_norm, ws.xn, M, D, cfg.norm_eps, dt, st));
+    LG_PROF(PC_EMBED_MISC, st, launch_rmsnorm(ws.h, layers[0].attn_norm, ws.xn, M, D, cfg.norm_eps, dt, st));
     for (int l = 0; l < L; ++l) {
         const Layer& ly = layers[l];
         char* kc = ws.kcache + (size_t)l * ws.layer_cache_bytes;
         char* vc = ws.vcache + (size_t)l * ws.layer_cache_bytes;
-        LG_TRY(gemm(ws.xn, M, 3 * D, D, ly.wqkv, nullptr, 0, &ks, nullptr, st));
+        LG_PROF(PC_GEMM_QKV, st, gemm(ws.xn, M, 3 * D, D, ly.wqkv, nullptr, 0, &ks, nullptr, st));
         QkvEpiArgs qa;
         qa.partial = ws.partial; qa.ksplit = ks; qa.M = M; qa.Tq = Tq; qa.D = D; qa.H = H; qa.hd = hd;
         qa.pos = pos; qa.freqs = freqs; qa.q = ws.q; qa.kcache = kc; qa.vcache = vc; qa.maxS = ws.max_seq; qa.dtype = dt;
-        LG_TRY(launch_qkv_epilogue(qa, st));
+        LG_PROF(PC_QKV_EPI, st, launch_qkv_epilogue(qa, st));
         AttnArgs aa;
         aa.q = ws.q; aa.kcache = kc; aa.vcache = vc; aa.out = ws.attn; aa.R = R; aa.Tq = Tq; aa.H = H; aa.hd = hd;
         aa.maxS = ws.max_seq; aa.pos = pos; aa.emb_mask = emb_mask; aa.B = B;
         aa.Tc = cfg.cls_token_num; aa.scale = 1.0f / sqrtf((float)hd); aa.dtype = dt;
-        LG_TRY(launch_attention(aa, st));
-        LG_TRY(gemm(ws.attn, M, D, D, ly.wo, nullptr, 0, &ks, nullptr, st));
-        LG_TRY(launch_residual_norm(ws.partial, ks, M, D, ws.h, ly.ffn_norm, ws.xn, cfg.norm_eps, dt, st));
-        LG_TRY(gemm(ws.xn, M, 2 * F, D, ly.w1, ly.w3, F, &ks, nullptr, st));
-        LG_TRY(launch_silu_mul(ws.partial, ks, M, F, ws.ff, dt, st));
-        LG_TRY(gemm(ws.ff, M, D, F, ly.w2, nullptr, 0, &ks, nullptr, st));
+        LG_PROF(PC_ATTENTION, st, launch_attention(aa, st));
+        LG_PROF(PC_GEMM_WO, st, gemm(ws.attn, M, D, D, ly.wo, nullptr, 0, &ks, nullptr, st));
+        LG_PROF(PC_RESNORM, st, launch_residual_norm(ws.partial, ks, M, D, ws.h, ly.ffn_norm, ws.xn, cfg.norm_eps, dt, st));
+        LG_PROF(PC_GEMM_W13, st, gemm(ws.xn, M, 2 * F, D, ly.w1, ly.w3, F, &ks, nullptr, st));
+        LG_PROF(PC_SILU, st, launch_silu_mul(ws.partial, ks, M, F, ws.ff, dt, st));
+        LG_PROF(PC_GEMM_W2, st, gemm(ws.ff, M, D, F, ly.w2, nullptr, 0, &ks, nullptr, st));
         const void* next_norm = (l + 1 < L) ? layers[l + 1].attn_norm : final_norm;
-        LG_TRY(launch_residual_norm(ws.partial, ks, M, D, ws.h, next_norm, ws.xn, cfg.norm_eps, dt, st));
+        LG_PROF(PC_RESNORM, st, launch_residual_norm(ws.partial, ks, M, D, ws.h, next_norm, ws.xn, cfg.norm_eps, dt, st));
     }
     // head on the last position only (generate.py:58 reads logits[:, -1])
     const void* xlast = ws.xn;
@@ -167,7 +228,9 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         xlast = ws.q;
     }
     (void)round_out;
+    prof_begin(PC_GEMM_HEAD, st);
     const int direct = gemm(xlast, R, V, D, output, nullptr, 0, &ks, logits_out, st);
+    prof_end(st);
     if (direct < 0) return direct;
     if (direct == 0) LG_TRY(launch_reduce_f32(ws.partial, ks, R, V, logits_out, st));
     return 0;
@@ -355,9 +418,33 @@ int lg_sample(const float* logits, int B, int V, int mix_cfg, int round_dtype, c
     return launch_sample(a, (cudaStream_t)stream);
 }
 
+static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, int B, int T, int S,
+                         const lg_sample_cfg* sc, int32_t* out_tokens, float* dbg_logits, const int32_t* teacher,
+                         cudaStream_t st);
+
 int lg_generate(lg_engine* e, const void* cond, const float* emb_mask, int B, int T, int S, const lg_sample_cfg* sc,
                 int32_t* out_tokens, float* dbg_logits, const int32_t* teacher, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+    // The loop runs on an engine-owned non-blocking stream forked from / joined to the caller's stream with
+    // events: the caller's stream may be the legacy default stream (torch's default), which cannot be captured
+    // into a CUDA graph. Semantics for the caller stay "asynchronous on the given stream".
+    cudaStream_t caller = (cudaStream_t)stream;
+    LG_REQUIRE(e, "lg_generate: null engine");
+    if (!e->work) {
+        LG_CUDA_OK(cudaStreamCreateWithFlags(&e->work, cudaStreamNonBlocking));
+        LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    }
+    LG_CUDA_OK(cudaEventRecord(e->ev_fork, caller));
+    LG_CUDA_OK(cudaStreamWaitEvent(e->work, e->ev_fork, 0));
+    const int rc = generate_impl(e, cond, emb_mask, B, T, S, sc, out_tokens, dbg_logits, teacher, e->work);
+    cudaEventRecord(e->ev_join, e->work);
+    cudaStreamWaitEvent(caller, e->ev_join, 0);
+    return rc;
+}
+
+static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, int B, int T, int S,
+                         const lg_sample_cfg* sc, int32_t* out_tokens, float* dbg_logits, const int32_t* teacher,
+                         cudaStream_t st) {
     LG_REQUIRE(cond && sc && out_tokens && B > 0 && S > 0, "lg_generate: bad argument");
     const bool use_cfg = sc->cfg_scale > 1.0f;  // generate.py:128
     const int R = use_cfg ? 2 * B : B;
@@ -387,16 +474,16 @@ int lg_generate(lg_engine* e, const void* cond, const float* emb_mask, int B, in
     LG_TRY(launch_set_counters(d_pos, T, d_step, 1, st));
     sa.step_dev = d_step;
     auto body = [&]() -> int {
-        LG_TRY(launch_embed(e->tok_emb, ws.tokens, B, R, -1, e->cfg.dim, e->cfg.dtype, ws.h, st));
+        LG_PROF(PC_EMBED_MISC, st, launch_embed(e->tok_emb, ws.tokens, B, R, -1, e->cfg.dim, e->cfg.dtype, ws.h, st));
         LG_TRY(e->forward(R, 1, PosArg{d_pos, 0}, emb_mask, B, ws.logits, false, st));
-        LG_TRY(launch_sample(sa, st));
-        LG_TRY(launch_advance(d_pos, d_step, st));
+        LG_PROF(PC_SAMPLE, st, launch_sample(sa, st));
+        LG_PROF(PC_EMBED_MISC, st, launch_advance(d_pos, d_step, st));
         return 0;
     };
     LG_TRY(body());  // first decode step runs eagerly (also sets every kernel attribute outside capture)
     const int remaining = S - 2;
     if (remaining <= 0) return 0;
-    if (!e->use_graph || remaining < 3) {
+    if (!e->use_graph || remaining < 3 || prof_enabled() || lg_debug_sync()) {
         for (int i = 0; i < remaining; ++i) LG_TRY(body());
         return 0;
     }
@@ -427,6 +514,30 @@ int lg_generate(lg_engine* e, const void* cond, const float* emb_mask, int B, in
     cudaGraphExecDestroy(exec);
     cudaGraphDestroy(graph);
     return ret;
+}
+
+int lg_profile_enable(int on) {
+    if (!on) prof_drain();
+    g_prof.on = on != 0;
+    return 0;
+}
+int lg_profile_reset(void) {
+    prof_drain();
+    for (int i = 0; i < PC_COUNT; ++i) { g_prof.total_ms[i] = 0; g_prof.count[i] = 0; }
+    return 0;
+}
+int lg_profile_read(int cls, double* total_ms, uint64_t* launches) {
+    LG_REQUIRE(cls >= 0 && cls < PC_COUNT && total_ms && launches, "lg_profile_read: bad argument");
+    prof_drain();
+    *total_ms = g_prof.total_ms[cls];
+    *launches = g_prof.count[cls];
+    return 0;
+}
+const char* lg_profile_class_name(int cls) {
+    static const char* names[PC_COUNT] = {"gemm_qkv", "qkv_rope_kvwrite", "attention", "gemm_wo", "residual_rmsnorm",
+                                          "gemm_w13", "silu_mul", "gemm_w2", "gemm_head", "sample", "embed_misc",
+                                          "vq_conv_gemm", "vq_gn_stats", "vq_gn_apply", "vq_attn", "vq_misc"};
+    return (cls >= 0 && cls < PC_COUNT) ? names[cls] : nullptr;
 }
 
 int lg_test_gemm(const void* x, const void* w, int M, int N, int K, int dtype, float* y, void* dev_scratch,

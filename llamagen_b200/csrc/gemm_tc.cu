@@ -1,0 +1,292 @@
+// Blackwell-native weight-streaming GEMM: tcgen05.mma (UMMA) with the accumulator in TMEM, operands staged
+// in shared memory by TMA (cp.async.bulk.tensor) through an mbarrier full/empty ring.
+//
+//   y[r, n] = sum_k x[r, k] * W[n, k]        (nn.Linear without bias, gpt.py:161-163,199-200,287)
+//
+// "Swap-AB" orientation for decode: the WEIGHT tile is the UMMA A operand (M = 128 output features = the
+// 128 TMEM lanes), the activations are the B operand (N = rows padded to 16, <= 256 = TMEM columns), so a
+// skinny batch never wastes the 128-row MMA shape and each CTA streams a [128 x Kslice] weight slab from
+// HBM exactly once. One CTA = one (n-tile, k-slice); split-K slabs (fp32) are reduced by the row-wise
+// epilogue kernels in xf_kernels.cu, exactly like the mma.sync path it replaces (gemm.cu).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected
+// lane) + TMEM allocator, warps 2..5 = epilogue (each owns the TMEM lane quarter (warp % 4)).
+#include "kernels.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+constexpr int kBlockN = 128;    // weight rows per CTA  (UMMA M)
+constexpr int kBlockK = 64;     // bf16 elements per k-block = 128 B = one swizzle-128B row
+constexpr int kStages = 6;
+constexpr int kThreads = 192;
+constexpr int kATileBytes = kBlockN * kBlockK * 2;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// UMMA instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor).
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockN >> 4) << 24);
+}
+
+struct TcArgs {
+    int M, N, K;          // activations rows, weight rows, reduction
+    int n_split;          // weight rows [0, n_split) come from map_wa, the rest from map_wb
+    int rpad;             // M rounded up to 16 (UMMA N)
+    int kblocks_per_split;
+    int tmem_cols;        // power of two >= max(32, rpad)
+    float* partial;       // [ksplit][M][N]
+};
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_wa,
+                                                              const __grid_constant__ CUtensorMap map_wb,
+                                                              const __grid_constant__ CUtensorMap map_x, TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // stage s: A tile at s*stage_bytes (1024-aligned), B tile right after
+    const int b_tile_bytes = a.rpad * kBlockK * 2;
+    const int stage_bytes = kATileBytes + ((b_tile_bytes + 1023) / 1024) * 1024;
+    uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kBlockN;
+    const int ks = blockIdx.y;
+    const int total_kb = (a.K + kBlockK - 1) / kBlockK;
+    const int kb0 = ks * a.kblocks_per_split;
+    const int nkb = max(0, min(a.kblocks_per_split, total_kb - kb0));
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wa) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wb) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_base_slot, (uint32_t)a.tmem_cols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            const bool second = n0 >= a.n_split;
+            const CUtensorMap* wmap = second ? &map_wb : &map_wa;
+            const int wrow = second ? n0 - a.n_split : n0;
+            const uint32_t tx = (uint32_t)(kATileBytes + b_tile_bytes);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kStages;
+                const uint32_t ph = (uint32_t)((i / kStages) & 1);
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], tx);
+                uint8_t* sa = tiles + s * stage_bytes;
+                tma_load_2d(sa, wmap, &full_bar[s], (kb0 + i) * kBlockK, wrow);
+                tma_load_2d(sa + kATileBytes, &map_x, &full_bar[s], (kb0 + i) * kBlockK, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = make_idesc(a.rpad);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % kStages;
+            const uint32_t ph = (uint32_t)((i / kStages) & 1);
+            mbar_wait(&full_bar[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(tiles + s * stage_bytes);
+                const uint64_t adesc = make_desc_sw128(sa);
+                const uint64_t bdesc = make_desc_sw128(sa + kATileBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (addr >> 4) field
+                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
+                }
+                umma_commit(&empty_bar[s]);                       // frees the smem slot when these MMAs retire
+                if (i == nkb - 1) umma_commit(tmem_full_bar);     // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: TMEM -> registers -> fp32 slab
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int n = n0 + q * 32 + lane;
+        float* out = a.partial + (size_t)ks * a.M * a.N;
+        if (nkb > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c0 = 0; c0 < a.rpad; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (n < a.N) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < a.M) out[(size_t)(c0 + j) * a.N + n] = __uint_as_float(v[j]);
+                }
+            }
+        } else if (n < a.N) {
+            for (int r = 0; r < a.M; ++r) out[(size_t)r * a.N + n] = 0.f;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (cols contiguous); box = [box_rows, 64 cols]; 128-byte swizzle; OOB -> zeros
+int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    LG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
+               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
+    return 0;
+}
+
+}  // namespace
+
+// Plan: number of k-slices so that (N/128) * ksplit approaches the SM count, with >= 2 k-blocks per slice.
+int gemm_tc_ksplit(int M, int N, int K) {
+    (void)M;
+    const int tiles = cdiv(N, kBlockN), kb = cdiv(K, kBlockK);
+    int ks = std::max(1, 148 / std::max(tiles, 1));
+    ks = std::min(ks, std::max(1, kb / 2));
+    return std::min(ks, 16);
+}
+
+bool gemm_tc_supported(int M, int N, int K, int dtype) {
+    return dtype == LG_DTYPE_BF16 && M >= 1 && M <= 256 && K % 8 == 0 && N % 2 == 0;
+}
+
+int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
+                    float* partial, int* ksplit_out, cudaStream_t st) {
+    LG_REQUIRE(gemm_tc_supported(M, N, K, LG_DTYPE_BF16), "gemm_tc: unsupported shape %d %d %d", M, N, K);
+    if (Wb == nullptr) { Wb = Wa; n_split = N; }
+    LG_REQUIRE(n_split % kBlockN == 0 || n_split == N, "gemm_tc: weight segment boundary %d must be a multiple of %d", n_split, kBlockN);
+    LG_REQUIRE(((uintptr_t)X & 15) == 0 && ((uintptr_t)Wa & 15) == 0 && ((uintptr_t)Wb & 15) == 0 && ldx % 8 == 0,
+               "gemm_tc: operands must be 16-byte aligned");
+    TcArgs a;
+    a.M = M; a.N = N; a.K = K; a.n_split = n_split;
+    a.rpad = ((M + 15) / 16) * 16;
+    const int ks = gemm_tc_ksplit(M, N, K);
+    const int kb = cdiv(K, kBlockK);
+    a.kblocks_per_split = cdiv(kb, ks);
+    a.tmem_cols = 32;
+    while (a.tmem_cols < a.rpad) a.tmem_cols *= 2;
+    a.partial = partial;
+    if (ksplit_out) *ksplit_out = ks;
+
+    CUtensorMap mwa, mwb, mx;
+    LG_TRY(make_map(&mwa, Wa, (uint64_t)std::min(n_split, N), (uint64_t)K, (uint64_t)K, kBlockN));
+    LG_TRY(make_map(&mwb, Wb, (uint64_t)std::max(N - n_split, Wb == Wa ? N : 1), (uint64_t)K, (uint64_t)K, kBlockN));
+    LG_TRY(make_map(&mx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, (uint32_t)a.rpad));
+
+    const int b_tile_bytes = a.rpad * kBlockK * 2;
+    const int stage_bytes = kATileBytes + ((b_tile_bytes + 1023) / 1024) * 1024;
+    const size_t smem = 1024 + (size_t)kStages * stage_bytes + (2 * kStages + 1) * sizeof(uint64_t) + 16;
+    static bool attr = false;
+    if (!attr) {
+        LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    LG_REQUIRE(smem <= 227 * 1024, "gemm_tc: shared memory %zu too large", smem);
+    dim3 grid(cdiv(N, kBlockN), ks);
+    gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mwa, mwb, mx, a);
+    LG_LAUNCH_CHECK();
+    return 0;
+}

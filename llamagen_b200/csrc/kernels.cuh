@@ -98,3 +98,23 @@ int launch_attention(const AttnArgs& a, cudaStream_t st);
 // *pos += 1; *step += 1  (device-side loop counters for graph replay)
 int launch_advance(int* pos, int* step, cudaStream_t st);
 int launch_set_counters(int* pos, int pos_v, int* step, int step_v, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// per-kernel-class device timing (bench.py's roofline leg): when enabled every launch site wrapped in
+// LG_PROF is bracketed by cudaEvents on the launching stream; graphs are bypassed while it is on.
+// ------------------------------------------------------------------------------------------------
+enum ProfClass {
+    PC_GEMM_QKV = 0, PC_QKV_EPI, PC_ATTENTION, PC_GEMM_WO, PC_RESNORM, PC_GEMM_W13, PC_SILU, PC_GEMM_W2,
+    PC_GEMM_HEAD, PC_SAMPLE, PC_EMBED_MISC, PC_VQ_CONV, PC_VQ_GN_STATS, PC_VQ_GN_APPLY, PC_VQ_ATTN, PC_VQ_MISC,
+    PC_COUNT
+};
+bool prof_enabled();
+void prof_begin(int cls, cudaStream_t st);
+void prof_end(cudaStream_t st);
+#define LG_PROF(cls, st, expr)                                                                   \
+    do {                                                                                         \
+        prof_begin((cls), (st));                                                                 \
+        int _pr = (expr);                                                                        \
+        prof_end((st));                                                                          \
+        if (_pr < 0) return _pr;                                                                 \
+    } while (0)

@@ -116,32 +116,34 @@ __global__ void lookup_postquant_kernel(const int32_t* __restrict__ codes, const
 // GroupNorm(32) statistics, pass 1: per (image, pixel-chunk) partial sum / sum-of-squares per group.
 // grid (splits, B), 256 threads; thread -> 8 contiguous channels (one 16-byte load per pixel).
 __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, int HW, int C, float* __restrict__ partial) {
+    // deterministic: per-thread partials go to shared memory and are combined in a fixed order (no atomics),
+    // so decode_code is bit-reproducible and batch-invariant.
+    __shared__ float part[256][17];   // [thread][8 sums + 8 squares], padded
     __shared__ float chs[512 * 2];
     const int b = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
-    const int tpp = C / 8;                       // threads per pixel
-    const int ppi = 256 / tpp;                   // pixels per iteration (tpp divides 256 for C in {32..512, pow2}); else partial use
+    const int tpp = C / 8;                       // threads per pixel (divides 256, checked on the host)
+    const int ppi = 256 / tpp;                   // pixels per iteration
     const int col = threadIdx.x % tpp, prow = threadIdx.x / tpp;
     const int per = (HW + splits - 1) / splits;
     const int p0 = split * per, p1 = min(HW, p0 + per);
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    if (prow < ppi) {
-        for (int p = p0 + prow; p < p1; p += ppi) {
-            float v[8];
-            VecLoad<bf16, 8>::load(x + ((size_t)b * HW + p) * C + col * 8, v);
+    for (int p = p0 + prow; p < p1; p += ppi) {
+        float v[8];
+        VecLoad<bf16, 8>::load(x + ((size_t)b * HW + p) * C + col * 8, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
-        }
+        for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
     }
-    for (int i = threadIdx.x; i < C * 2; i += 256) chs[i] = 0.f;
-    __syncthreads();
-    if (prow < ppi) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            atomicAdd(&chs[(col * 8 + i) * 2], s[i]);
-            atomicAdd(&chs[(col * 8 + i) * 2 + 1], q[i]);
-        }
+    for (int i = 0; i < 8; ++i) { part[threadIdx.x][i] = s[i]; part[threadIdx.x][8 + i] = q[i]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const int cc = c / 8, ci = c % 8;
+        float cs = 0.f, cq = 0.f;
+        for (int pr = 0; pr < ppi; ++pr) { cs += part[pr * tpp + cc][ci]; cq += part[pr * tpp + cc][8 + ci]; }
+        chs[c * 2] = cs;
+        chs[c * 2 + 1] = cq;
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -429,15 +431,20 @@ int run_conv(const ConvW& cw, const bf16* in, int B, int Hin, int Win, int up, c
     e.bias = cw.bias; e.residual = residual; e.ldr = cw.cout; e.out_bf = out_bf; e.ldo = cw.cout; e.scale = 1.f;
     e.N = cw.cout;
     if (out_nchw) { e.out_f32 = out_nchw; e.nchw = 1; e.hw = Hout * Wout; e.out_bf = nullptr; }
-    return launch_vq_gemm(al, bw, M, cw.cout, K, 1, e, st);
+    LG_PROF(PC_VQ_CONV, st, launch_vq_gemm(al, bw, M, cw.cout, K, 1, e, st));
+    return 0;
 }
 
 int run_gn(const NormW& nw, const bf16* x, bf16* y, int B, int HW, int swish, float* gnbuf, cudaStream_t st) {
     int splits = (int)std::min<long long>(64, std::max<long long>(1, (long long)HW * nw.c / 8 / 2048));
+    prof_begin(PC_VQ_GN_STATS, st);
     gn_stats_kernel<<<dim3(splits, B), 256, 0, st>>>(x, HW, nw.c, gnbuf);
+    prof_end(st);
     LG_LAUNCH_CHECK();
     int chunks = (int)std::min<long long>(1024, std::max<long long>(1, (long long)HW * (nw.c / 8) / 1024));
+    prof_begin(PC_VQ_GN_APPLY, st);
     gn_apply_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, gnbuf, splits, nw.gamma, nw.beta, y, HW, nw.c, swish);
+    prof_end(st);
     LG_LAUNCH_CHECK();
     return 0;
 }
@@ -466,14 +473,14 @@ int run_attn(const AttnW& a, VqWs& w, int B, int H, int W, cudaStream_t st) {
         mma::DenseA al{w.T, C, 0, B * N};
         mma::BRows bw{a.qk.w, a.qk.w, 2 * C, C, 0, 2 * C};
         EpiVq e{}; e.bias = a.qk.bias; e.out_bf = w.U; e.ldo = 2 * C; e.scale = 1.f; e.N = 2 * C;
-        LG_TRY(launch_vq_gemm(al, bw, B * N, 2 * C, C, 1, e, st));
+        LG_PROF(PC_VQ_ATTN, st, launch_vq_gemm(al, bw, B * N, 2 * C, C, 1, e, st));
     }
     {   // V^T[b] = Wv * hn[b]^T + bv  -> VT [B][C][N]   (A = Wv shared, "weights" = hn[b])
         mma::DenseA al{a.v.w, C, 0, C};
         mma::BRows bw{w.T, w.T, N, C, (long long)N * C, N};
         EpiVq e{}; e.bias = a.v.bias; e.bias_by_row = 1; e.out_bf = w.VT; e.ldo = N; e.out_batch_stride = (long long)C * N;
         e.scale = 1.f; e.N = N;
-        LG_TRY(launch_vq_gemm(al, bw, C, N, C, B, e, st));
+        LG_PROF(PC_VQ_ATTN, st, launch_vq_gemm(al, bw, C, N, C, B, e, st));
     }
     const float scale = 1.0f / sqrtf((float)C);                                   // int(c)**(-0.5), :338
     for (int b0 = 0; b0 < B; b0 += w.attn_bc) {
@@ -483,16 +490,18 @@ int run_attn(const AttnW& a, VqWs& w, int B, int H, int W, cudaStream_t st) {
             mma::BRows bw{w.U + (size_t)b0 * N * 2 * C + C, nullptr, N, 2 * C, (long long)N * 2 * C, N};
             bw.Wb = bw.Wa;
             EpiVq e{}; e.out_f32 = w.S; e.ldo = N; e.out_batch_stride = (long long)N * N; e.scale = scale; e.N = N;
-            LG_TRY(launch_vq_gemm(al, bw, N, N, C, bc, e, st));
+            LG_PROF(PC_VQ_ATTN, st, launch_vq_gemm(al, bw, N, N, C, bc, e, st));
         }
+        prof_begin(PC_VQ_ATTN, st);
         softmax_rows_kernel<<<bc * N, 256, 0, st>>>(w.S, w.P, N);
+        prof_end(st);
         LG_LAUNCH_CHECK();
         {   // O[b] = P[b] V[b]  -> T [B*N, C]
             mma::DenseA al{w.P, N, (long long)N * N, N};
             mma::BRows bw{w.VT + (size_t)b0 * C * N, nullptr, C, N, (long long)C * N, C};
             bw.Wb = bw.Wa;
             EpiVq e{}; e.out_bf = w.T + (size_t)b0 * N * C; e.ldo = C; e.out_batch_stride = (long long)N * C; e.scale = 1.f; e.N = C;
-            LG_TRY(launch_vq_gemm(al, bw, N, C, N, bc, e, st));
+            LG_PROF(PC_VQ_ATTN, st, launch_vq_gemm(al, bw, N, C, N, bc, e, st));
         }
     }
     // x = x + proj_out(O)

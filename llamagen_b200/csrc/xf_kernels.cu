@@ -198,7 +198,9 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
     const int stride = nwarps * KPW;
-    for (int j0 = warp * KPW + g; j0 < nkeys; j0 += stride * UNROLL) {
+    // the trip count must be warp-uniform: the full-mask shuffles below need all 32 lanes
+    for (int jb = warp * KPW; jb < nkeys; jb += stride * UNROLL) {
+        const int j0 = jb + g;
         float kv[UNROLL][VEC], vv[UNROLL][VEC];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {

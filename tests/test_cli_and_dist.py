@@ -1,0 +1,98 @@
+"""CPU: CLI flag parity with the reference scripts, and the N>1 host logic (weight broadcast, sharding, seeds)
+over gloo with world_size 2."""
+import os
+import re
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _ref_flags(path):
+    return set(re.findall(r'add_argument\(\s*"(--[a-z0-9\-]+)"', open(path).read()))
+
+
+@pytest.mark.parametrize("script", ["sample_c2i", "sample_t2i", "sample_c2i_ddp"])
+def test_cli_accepts_every_reference_flag(reference_path, script):
+    import importlib
+    mod = importlib.import_module(f"llamagen_b200.sample.{script}")
+    ours = {a for act in mod.build_parser()._actions for a in act.option_strings}
+    ref = _ref_flags(os.path.join(reference_path, "autoregressive", "sample", f"{script}.py"))
+    assert ref <= ours, f"missing flags: {sorted(ref - ours)}"
+
+
+def test_cli_defaults_match_reference_text():
+    from llamagen_b200.sample import sample_c2i, sample_t2i
+    a = sample_c2i.build_parser().parse_args([])
+    assert (a.gpt_model, a.image_size, a.cfg_scale, a.top_k, a.precision, a.cls_token_num) == ("GPT-B", 384, 4.0, 2000, "bf16", 1)
+    b = sample_t2i.build_parser().parse_args([])
+    assert (b.gpt_model, b.image_size, b.cfg_scale, b.top_k, b.cls_token_num, b.t5_feature_max_len) == ("GPT-XL", 512, 7.5, 1000, 120, 120)
+
+
+def test_checkpoint_key_dispatch():
+    from llamagen_b200.sample.common import pick_model_weight
+    sd = {"w": 1}
+    assert pick_model_weight(sd, True) is sd
+    for k in ("model", "module", "state_dict"):
+        assert pick_model_weight({k: sd}, False) is sd
+    with pytest.raises(Exception, match="please check model weight"):
+        pick_model_weight({"other": sd}, False)
+
+
+def test_shard_and_index_helpers():
+    from llamagen_b200 import distributed as lgd
+    for total, world in ((256, 8), (10, 4), (3, 8)):
+        covered = []
+        for r in range(world):
+            lo, hi = lgd.shard_range(total, r, world)
+            covered += list(range(lo, hi))
+        assert covered == list(range(total))
+    assert lgd.rank_seed(3, 5, 8) == 29
+    idx = sorted(lgd.image_index(i, r, 4, 8) for r in range(4) for i in range(2))
+    assert idx == list(range(8, 16))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    from llamagen_b200 import distributed as lgd
+    from llamagen_b200.gpt import ModelArgs, Transformer
+    r, w, _ = lgd.init_from_env("gloo")
+    torch.manual_seed(100 + rank)                       # ranks start with DIFFERENT weights
+    m = Transformer(ModelArgs(n_layer=1, n_head=1, dim=64, vocab_size=32, block_size=4, num_classes=3))
+    n = lgd.broadcast_module(m, src=0)
+    digest = torch.cat([p.reshape(-1) for p in m.state_dict().values()]).double().sum().item()
+    q.put((r, w, n, digest, lgd.rank_seed(0, r, w)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_weight_broadcast_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, w0, n0, d0, s0), (r1, w1, n1, d1, s1) = res
+    assert (r0, r1, w0, w1) == (0, 1, 2, 2)
+    assert n0 == n1 and n0 > 0
+    assert d0 == d1, "weights differ after the broadcast"
+    assert (s0, s1) == (0, 1)

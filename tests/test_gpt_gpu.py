@@ -90,20 +90,35 @@ def test_gpt_b_fp32_greedy_bit_exact_vs_oracle():
     assert torch.equal(toks, ref_t)
 
 
+def _bf16_parity(m, cond, S):
+    """bf16 engine vs the oracle, teacher-forced on the fp32 oracle's greedy stream. The tolerance is calibrated
+    on the spot: the engine may deviate from the fp32 oracle (same bf16-rounded weights) by at most 1.5x the
+    ORACLE'S OWN bf16-vs-fp32 spread on these CFG-mixed logits (cfg 4.0 amplifies rounding noise ~7x; for GPT-L
+    that spread is max 0.22 / mean 0.04 at logit std 3.1, abs-max 13), and from the bf16 oracle (like for like)
+    by the same bound; arg-max must agree wherever the fp32 oracle's top-1/top-2 gap exceeds 2x the bound."""
+    cfg = oracle_cfg(m)
+    ref_t, ref_l = GPTOracle(cpu_state(m, torch.float32), cfg).generate(cond, S, cfg_scale=4.0, sample_logits=False)
+    _, b16_l = GPTOracle(cpu_state(m), cfg).generate(cond, S, cfg_scale=4.0, sample_logits=False, teacher=ref_t)
+    spread_max = (b16_l - ref_l).abs().max().item()
+    spread_mean = (b16_l - ref_l).abs().mean().item()
+    tol_max, tol_mean = 1.5 * spread_max + 0.02, 1.5 * spread_mean + 0.005
+    toks, logits = _gen(m, cond, S, None, cfg_scale=4.0, teacher=ref_t.clone())
+    for other in (ref_l, b16_l):
+        err = (logits - other).abs()
+        assert err.max().item() <= tol_max, (err.max().item(), tol_max)
+        assert err.mean().item() <= tol_mean, (err.mean().item(), tol_mean)
+    decisive = top2_gap(ref_l) > 2 * tol_max
+    assert torch.equal(logits.argmax(-1)[decisive], ref_l.argmax(-1)[decisive])
+    assert torch.equal(toks.t()[decisive], ref_t.t()[decisive])
+
+
 @pytest.mark.parametrize("B", [1, 9, 40])
 def test_gpt_l_bf16_teacher_forced(B):
     """GPT-L bf16 (BASELINE config C2 model): B=1 exercises the skinny CUDA-core GEMM (R=2), B=9 / 40 the
-    tensor-core path with BM=32 / 128 tiles. Reference = fp32 oracle on the same bf16-rounded weights."""
+    tensor-core path with BM=32 / 128 tiles."""
     m = _registry_model("GPT-L", torch.bfloat16, 1, block_size=256, vocab_size=16384)
     torch.manual_seed(B)
-    cond = torch.randint(0, 1000, (B,))
-    S = 6
-    orc = GPTOracle(cpu_state(m, torch.float32), oracle_cfg(m))
-    ref_t, ref_l = orc.generate(cond, S, cfg_scale=4.0, sample_logits=False)
-    toks, logits = _gen(m, cond, S, None, cfg_scale=4.0, teacher=ref_t.clone())
-    assert (logits - ref_l).abs().max().item() <= BF16_TOL
-    decisive = top2_gap(ref_l) > 2 * BF16_TOL
-    assert torch.equal(logits.argmax(-1)[decisive], ref_l.argmax(-1)[decisive])
+    _bf16_parity(m, torch.randint(0, 1000, (B,)), 6)
 
 
 def test_gpt_3b_head_dim_100_bf16():
@@ -113,12 +128,7 @@ def test_gpt_3b_head_dim_100_bf16():
     m = Transformer(ModelArgs(n_layer=4, n_head=32, dim=3200, block_size=576, vocab_size=16384))
     m.output.weight.data.normal_(std=0.02)
     m = m.to(device="cuda", dtype=torch.bfloat16).eval()
-    cond = torch.tensor([1, 2, 3])
-    S = 5
-    orc = GPTOracle(cpu_state(m, torch.float32), oracle_cfg(m))
-    ref_t, ref_l = orc.generate(cond, S, cfg_scale=4.0, sample_logits=False)
-    toks, logits = _gen(m, cond, S, None, cfg_scale=4.0, teacher=ref_t.clone())
-    assert (logits - ref_l).abs().max().item() <= BF16_TOL
+    _bf16_parity(m, torch.tensor([1, 2, 3]), 5)
 
 
 def test_forward_api_matches_generate_path():
