@@ -48,6 +48,29 @@ def parse():
     return p.parse_args()
 
 
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def host_cores():
+    """Cores this process may actually use: affinity mask capped by the cgroup CPU quota (a container can
+    show 128 logical CPUs while being throttled to a few; oversubscribing OpenMP there is catastrophic)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = max(1, min(n, q // per))
+        except Exception:
+            pass
+    return n
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -144,8 +167,9 @@ def run_reference(args, rank):
     from oracle import GPTOracle, VQOracle
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
+    log(f"reference arm: {cores} host threads (os.cpu_count()={os.cpu_count()})")
     torch.manual_seed(args.seed)
     g = args.image_size // 16
     S = g * g
@@ -187,7 +211,8 @@ def run_reference(args, rank):
 
     with torch.no_grad():
         for _ in range(args.warmup):
-            one_sample()
+            v, d = one_sample()
+            log(f"reference warmup sample: {v:.4f} img/s {d}")
         vals, detail = [], None
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -271,8 +296,12 @@ def run_ours(args):
         return ms
 
     labels_dev = torch.randint(0, 1000, (B,), device=dev)
+    log(f"rank {rank}: models ready, warming up")
     for _ in range(max(args.warmup, 3)):
+        t0 = time.perf_counter()
         step_resident(labels_dev)
+        torch.cuda.synchronize()
+        log(f"rank {rank}: warmup step {time.perf_counter() - t0:.3f} s")
     step_e2e()
     torch.cuda.synchronize()
 
@@ -284,6 +313,7 @@ def run_ours(args):
     launches = int(lib.lg_launch_count())
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    log(f"rank {rank}: timed {ms / args.steps:.1f} ms/step resident, {ms_e2e / args.steps:.1f} ms/step e2e")
     value = world * B * args.steps / (ms / 1000.0)
     e2e_value = world * B * args.steps / (ms_e2e / 1000.0)
 
@@ -302,6 +332,7 @@ def run_ours(args):
     # ---------------- roofline leg: per-kernel-class CUDA-event timing of one extra (untimed) step, rank 0 only
     if rank == 0 and not args.no_roofline:
         pk = peaks()
+        log("roofline leg: profiling one step per kernel class")
         lib.lg_profile_reset()
         lib.lg_profile_enable(1)
         step_resident(labels_dev)
@@ -345,15 +376,16 @@ def run_ours(args):
 
     # ---------------- CPU baseline leg (rank 0, N=1 only): bounded sample of the same workload on the host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                            "--gpt-model", args.gpt_model, "--image-size", str(args.image_size), "--batch", str(B)],
-                           capture_output=True, text=True, timeout=1500, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
         try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                                "--gpt-model", args.gpt_model, "--image-size", str(args.image_size), "--batch", str(B)],
+                               capture_output=True, text=True, timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
             ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
             line["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as ex:   # never silently drop the leg
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"failed: {ex}: {r.stderr[-300:]}"}
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "port",
+                                    "sample": f"failed: {type(ex).__name__}: {str(ex)[-300:]}"}
+        log("cpu baseline leg done")
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,0 +1,236 @@
+// Decode attention (one query per sequence row) for bf16 KV caches: the K and V prefixes of one (row, head)
+// are contiguous [c, hd] streams in HBM, so they are pulled by TMA (cp.async.bulk.tensor, 128-byte swizzle)
+// through a 3-stage mbarrier ring — no registers are spent on loads in flight — and the two tiny matrix
+// products (q.K^T and P.V, M = 1 query padded to the m16 MMA shape) run on the tensor cores with ldmatrix
+// operands; softmax stays fp32 in registers (FlashAttention-2 style register reuse of P).
+//
+// Replaces, for Tq == 1, gpt.py:229-236 (repeat_interleave copies + masked SDPA over all max_seq slots):
+// only the valid prefix [0, pos] is read. Mask rule: generate.py:154-163 (emb_masks on the condition keys).
+#include "kernels.cuh"
+#include "tma_utils.cuh"
+
+namespace {
+
+using namespace tma;
+
+constexpr int kKC = 64;        // keys per stage
+constexpr int kStagesA = 3;
+constexpr int kWarps = 4;      // each warp owns 16 keys of a stage
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+struct AttnTmaArgs {
+    const bf16* q;     // [R, D]
+    bf16* out;         // [R, D]
+    int R, H, maxS;
+    const int* pos_dev; int pos_value;
+    long long row_base;          // first cache row of this layer inside the tensor maps
+    const float* emb_mask; int B, Tc;
+    float scale;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kWarps * 32) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
+                                                               const __grid_constant__ CUtensorMap vmap, AttnTmaArgs a) {
+    constexpr int NSUB = HD / 64;                 // 128-byte-wide sub-tiles per row
+    constexpr int SUB_BYTES = kKC * 128;          // one [64 keys][64 dims] bf16 sub-tile
+    constexpr int TILE_BYTES = NSUB * SUB_BYTES;  // K (or V) of one stage
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStagesA * 2 * TILE_BYTES);
+    float* merge = reinterpret_cast<float*>(full_bar + kStagesA);   // [kWarps][HD + 2]
+
+    const int h = blockIdx.x, r = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+    const int qpos = (a.pos_dev ? *a.pos_dev : 0) + a.pos_value;
+    const int nkeys = qpos + 1;
+    const int nchunks = (nkeys + kKC - 1) / kKC;
+    const long long row0 = a.row_base + ((long long)r * a.H + h) * a.maxS;
+    const int D = a.H * HD;
+
+    if (threadIdx.x == 0) {
+        prefetch_map(&kmap);
+        prefetch_map(&vmap);
+        for (int s = 0; s < kStagesA; ++s) mbar_init(&full_bar[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int ci) {
+        const int s = ci % kStagesA;
+        uint8_t* kt = tiles + s * 2 * TILE_BYTES;
+        uint8_t* vt = kt + TILE_BYTES;
+        mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+            load_2d(kt + sub * SUB_BYTES, &kmap, &full_bar[s], sub * 64, (int)(row0 + (long long)ci * kKC));
+            load_2d(vt + sub * SUB_BYTES, &vmap, &full_bar[s], sub * 64, (int)(row0 + (long long)ci * kKC));
+        }
+    };
+    if (threadIdx.x == 0)
+        for (int ci = 0; ci < min(kStagesA, nchunks); ++ci) issue(ci);
+
+    // q as the A operand of m16n8k16: only MMA row 0 (lanes with g == 0) is real, the other 15 rows are zero
+    uint32_t qa[HD / 16][2];
+    const bf16* qp = a.q + (size_t)r * D + (size_t)h * HD;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+        qa[kk][0] = 0; qa[kk][1] = 0;
+        if (g == 0) {
+            qa[kk][0] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + tg * 2);
+            qa[kk][1] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + 8 + tg * 2);
+        }
+    }
+    const float* mrow = a.emb_mask ? a.emb_mask + (size_t)(r % a.B) * a.Tc : nullptr;
+
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
+    float mx = -INFINITY, l = 0.f;
+
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int s = ci % kStagesA;
+        mbar_wait(&full_bar[s], (uint32_t)((ci / kStagesA) & 1));
+        const uint32_t kt = smem_u32(tiles + s * 2 * TILE_BYTES);
+        const uint32_t vt = kt + TILE_BYTES;
+        const int j0 = ci * kKC + warp * 16;          // this warp's 16 keys
+        if (j0 < nkeys) {                              // warp-uniform
+            // ---- S = q K^T for 16 keys (two n8 tiles)
+            float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk) {
+                uint32_t b0, b1, b2, b3;
+                const int row = warp * 16 + (lane & 7) + ((lane >> 4) << 3);
+                const int chunk = (kk * 2 + ((lane >> 3) & 1)) & 7;
+                ldsm_x4(kt + (kk / 4) * SUB_BYTES + swz(row, chunk), b0, b1, b2, b3);
+                mma16816(sc[0], qa[kk][0], 0u, qa[kk][1], 0u, b0, b1);
+                mma16816(sc[1], qa[kk][0], 0u, qa[kk][1], 0u, b2, b3);
+            }
+            // ---- online softmax on MMA row 0 (held by the quad g == 0; other quads carry zero rows)
+            float pv[4];
+            float lmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = j0 + (i >> 1) * 8 + tg * 2 + (i & 1);
+                bool vis = j < nkeys;
+                if (vis && mrow && j < a.Tc && j != qpos) vis = mrow[j] != 0.f;
+                pv[i] = vis ? sc[i >> 1][i & 1] * a.scale : -INFINITY;
+                lmax = fmaxf(lmax, pv[i]);
+            }
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, 1));
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, 2));
+            const float mn = fmaxf(mx, lmax);
+            float corr = 1.f, lsum = 0.f;
+            if (mn != -INFINITY) {
+                corr = __expf(mx - mn);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { pv[i] = __expf(pv[i] - mn); lsum += pv[i]; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pv[i] = 0.f;
+            }
+            lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+            lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+            l = l * corr + lsum;
+            mx = mn;
+#pragma unroll
+            for (int i = 0; i < HD / 8; ++i) { o[i][0] *= corr; o[i][1] *= corr; }
+            // ---- O += P V : P (bf16) is already in A-fragment layout (C layout of S == A layout of P)
+            const uint32_t pa0 = pack_bf16(pv[0], pv[1]);   // keys tg*2, +1
+            const uint32_t pa2 = pack_bf16(pv[2], pv[3]);   // keys 8 + tg*2, +1
+#pragma unroll
+            for (int np = 0; np < HD / 16; ++np) {
+                uint32_t b0, b1, b2, b3;
+                const int row = warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                const int chunk = (np * 2 + (lane >> 4)) & 7;
+                ldsm_x4_t(vt + (np / 4) * SUB_BYTES + swz(row, chunk), b0, b1, b2, b3);
+                mma16816(o[2 * np], pa0, 0u, pa2, 0u, b0, b1);
+                mma16816(o[2 * np + 1], pa0, 0u, pa2, 0u, b2, b3);
+            }
+        }
+        __syncthreads();                                // every warp is done with stage s
+        if (threadIdx.x == 0 && ci + kStagesA < nchunks) issue(ci + kStagesA);
+    }
+
+    // ---- merge the four warps (each saw a disjoint key subset)
+    float* wrow = merge + warp * (HD + 2);
+    if (g == 0) {
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+            wrow[i * 8 + tg * 2] = o[i][0];
+            wrow[i * 8 + tg * 2 + 1] = o[i][1];
+        }
+        if (tg == 0) { wrow[HD] = mx; wrow[HD + 1] = l; }
+    }
+    __syncthreads();
+    bf16* op = a.out + (size_t)r * D + (size_t)h * HD;
+    for (int e = threadIdx.x; e < HD; e += blockDim.x) {
+        float M_ = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) M_ = fmaxf(M_, merge[w * (HD + 2) + HD]);
+        float L = 0.f, O = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const float mw = merge[w * (HD + 2) + HD];
+            const float c = mw == -INFINITY ? 0.f : __expf(mw - M_);
+            L += merge[w * (HD + 2) + HD + 1] * c;
+            O += merge[w * (HD + 2) + e] * c;
+        }
+        op[e] = __float2bfloat16_rn(O / L);
+    }
+}
+
+template <int HD>
+int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnTmaArgs& a, cudaStream_t st) {
+    constexpr int TILE_BYTES = (HD / 64) * kKC * 128;
+    const size_t smem = 1024 + (size_t)kStagesA * 2 * TILE_BYTES + kStagesA * sizeof(uint64_t) + kWarps * (HD + 2) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        LG_CUDA_OK(cudaFuncSetAttribute(attn_tma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid(a.H, a.R);
+    attn_tma_kernel<HD><<<grid, kWarps * 32, smem, st>>>(kmap, vmap, a);
+    LG_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+// KV-cache tensor maps: the whole K (or V) region of the workspace as one [rows, hd] bf16 matrix
+int attn_tma_make_map(void* map_out, const void* cache_base, long long total_rows, int hd) {
+    return tma::make_map_2d(reinterpret_cast<CUtensorMap*>(map_out), cache_base, (uint64_t)total_rows, (uint64_t)hd, (uint64_t)hd,
+                            kKC, 64);
+}
+
+bool attn_tma_supported(const AttnArgs& a) {
+    return a.dtype == LG_DTYPE_BF16 && a.Tq == 1 && (a.hd == 64 || a.hd == 128) && a.kmap && a.vmap && a.R <= 65535;
+}
+
+int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
+    AttnTmaArgs t;
+    t.q = (const bf16*)a.q; t.out = (bf16*)a.out; t.R = a.R; t.H = a.H; t.maxS = a.maxS;
+    t.pos_dev = a.pos.dev; t.pos_value = a.pos.value; t.row_base = a.cache_row_base;
+    t.emb_mask = a.emb_mask; t.B = a.B; t.Tc = a.Tc; t.scale = a.scale;
+    const CUtensorMap& km = *reinterpret_cast<const CUtensorMap*>(a.kmap);
+    const CUtensorMap& vm = *reinterpret_cast<const CUtensorMap*>(a.vmap);
+    if (a.hd == 64) return launch_t<64>(km, vm, t, st);
+    return launch_t<128>(km, vm, t, st);
+}

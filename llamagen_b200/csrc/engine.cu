@@ -28,6 +28,11 @@ int lg_fail(const char* fmt, ...) {
     return -1;
 }
 std::atomic<uint64_t> g_lg_launches{0};
+int lg_env_flag(const char* name, int dflt) {
+    const char* e = getenv(name);
+    if (!e || !e[0]) return dflt;
+    return atoi(e);
+}
 bool lg_debug_sync() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("LG_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -105,6 +110,9 @@ struct Workspace {
     int32_t* tokens = nullptr;
     int* counters = nullptr;  // [0] = pos, [1] = step
     size_t layer_cache_bytes = 0;
+    alignas(64) unsigned char kmap[128];   // CUtensorMap over the K / V cache regions (bf16 only)
+    alignas(64) unsigned char vmap[128];
+    bool have_maps = false;
 };
 
 struct Layer {
@@ -212,6 +220,10 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         aa.q = ws.q; aa.kcache = kc; aa.vcache = vc; aa.out = ws.attn; aa.R = R; aa.Tq = Tq; aa.H = H; aa.hd = hd;
         aa.maxS = ws.max_seq; aa.pos = pos; aa.emb_mask = emb_mask; aa.B = B;
         aa.Tc = cfg.cls_token_num; aa.scale = 1.0f / sqrtf((float)hd); aa.dtype = dt;
+        if (ws.have_maps) {
+            aa.kmap = ws.kmap; aa.vmap = ws.vmap;
+            aa.cache_row_base = (long long)l * ws.rows * H * ws.max_seq;
+        }
         LG_PROF(PC_ATTENTION, st, launch_attention(aa, st));
         LG_PROF(PC_GEMM_WO, st, gemm(ws.attn, M, D, D, ly.wo, nullptr, 0, &ks, nullptr, st));
         LG_PROF(PC_RESNORM, st, launch_residual_norm(ws.partial, ks, M, D, ws.h, ly.ffn_norm, ws.xn, cfg.norm_eps, dt, st));
@@ -365,6 +377,18 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
     LG_REQUIRE(bytes >= needb, "workspace too small: %zu < %zu", bytes, needb);
     tmp.base = (char*)dev_ws;
     tmp.bytes = bytes;
+    // The reference zero-fills the KV cache (gpt.py:174-175). The tensor-core attention multiplies masked
+    // probabilities (exactly 0) with whatever sits in not-yet-written V rows, so those rows must be finite.
+    LG_CUDA_OK(cudaMemset(tmp.kcache, 0, 2 * ((tmp.layer_cache_bytes * e->cfg.n_layer + 255) / 256 * 256)));
+    tmp.have_maps = false;
+    if (e->cfg.dtype == LG_DTYPE_BF16 && (e->hd == 64 || e->hd == 128)) {
+        const long long total_rows = (long long)e->cfg.n_layer * rows * e->cfg.n_head * max_seq;
+        if (total_rows < (1ll << 31)) {
+            LG_TRY(attn_tma_make_map(tmp.kmap, tmp.kcache, total_rows, e->hd));
+            LG_TRY(attn_tma_make_map(tmp.vmap, tmp.vcache, total_rows, e->hd));
+            tmp.have_maps = true;
+        }
+    }
     e->ws = tmp;
     return 0;
 }

@@ -87,13 +87,21 @@ __global__ void __launch_bounds__(kSkinnyWarps * 32) gemm_skinny_kernel(const T*
 
 struct Plan {
     bool skinny;
+    bool tc;      // tcgen05 / TMEM / TMA kernel (gemm_tc.cu)
     int bm;       // mma tile rows
     int ksplit;
 };
 
 Plan make_plan(int M, int N, int K, int dtype) {
     Plan p;
+    p.tc = false;
     p.skinny = (dtype == LG_DTYPE_F32) || M <= kSkinnyRT;
+    if (!p.skinny && lg_env_flag("LG_GEMM_TC", 0) && gemm_tc_supported(M, N, K, dtype) && N % 128 == 0) {
+        p.tc = true;
+        p.bm = 0;
+        p.ksplit = gemm_tc_ksplit(M, N, K);
+        return p;
+    }
     if (p.skinny) {
         p.bm = kSkinnyRT;
         const long long ctas = (long long)cdiv(N, 2 * kSkinnyWarps) * cdiv(M, kSkinnyRT);
@@ -145,6 +153,10 @@ int gemm_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_s
         }
         LG_LAUNCH_CHECK();
         return 0;
+    }
+    if (p.tc) {
+        if (n_split % 128 != 0 && n_split != N) return lg_fail("gemm: weight segment boundary %d not tile aligned", n_split);
+        return gemm_tc_partial(X, ldx, Wa, Wb, n_split, M, N, K, partial, nullptr, st);
     }
     mma::DenseA al{(const bf16*)X, ldx, 0, M};
     mma::BRows bw{(const bf16*)Wa, (const bf16*)Wb, n_split, K, 0, N};

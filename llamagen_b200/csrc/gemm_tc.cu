@@ -12,7 +12,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected
 // lane) + TMEM allocator, warps 2..5 = epilogue (each owns the TMEM lane quarter (warp % 4)).
 #include "kernels.cuh"
-#include <cuda.h>
+#include "tma_utils.cuh"
 #include <mutex>
 #include <unordered_map>
 
@@ -20,46 +20,12 @@ namespace {
 
 constexpr int kBlockN = 128;    // weight rows per CTA  (UMMA M)
 constexpr int kBlockK = 64;     // bf16 elements per k-block = 128 B = one swizzle-128B row
-constexpr int kStages = 6;
+constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr int kATileBytes = kBlockN * kBlockK * 2;   // 16 KB
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace tma;
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -102,6 +68,7 @@ struct TcArgs {
     int rpad;             // M rounded up to 16 (UMMA N)
     int kblocks_per_split;
     int tmem_cols;        // power of two >= max(32, rpad)
+    int stages;           // smem ring depth (<= kMaxStages), sized to fit 227 KB
     float* partial;       // [ksplit][M][N]
 };
 
@@ -113,9 +80,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int b_tile_bytes = a.rpad * kBlockK * 2;
     const int stage_bytes = kATileBytes + ((b_tile_bytes + 1023) / 1024) * 1024;
     uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int kStages = a.stages;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStages * stage_bytes);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -126,12 +94,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int nkb = max(0, min(a.kblocks_per_split, total_kb - kb0));
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wa) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wb) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        prefetch_map(&map_wa);
+        prefetch_map(&map_wb);
+        prefetch_map(&map_x);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_slot, (uint32_t)a.tmem_cols);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -152,8 +120,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 mbar_expect_tx(&full_bar[s], tx);
                 uint8_t* sa = tiles + s * stage_bytes;
-                tma_load_2d(sa, wmap, &full_bar[s], (kb0 + i) * kBlockK, wrow);
-                tma_load_2d(sa + kATileBytes, &map_x, &full_bar[s], (kb0 + i) * kBlockK, 0);
+                load_2d(sa, wmap, &full_bar[s], (kb0 + i) * kBlockK, wrow);
+                load_2d(sa + kATileBytes, &map_x, &full_bar[s], (kb0 + i) * kBlockK, 0);
             }
         }
     } else if (warp == 1) {
@@ -205,11 +173,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------- host side
+}  // namespace
+
+namespace tma {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
+static EncodeTiledFn get_encode() {
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;
     std::call_once(once, [] {
@@ -221,24 +191,37 @@ EncodeTiledFn get_encode() {
     });
     return fn;
 }
-
-// 2-D bf16 row-major [rows, cols] (cols contiguous); box = [box_rows, 64 cols]; 128-byte swizzle; OOB -> zeros
-int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                uint32_t box_cols) {
     EncodeTiledFn enc = get_encode();
     LG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld_elems * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    LG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
-               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
+    LG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows, box_cols);
     return 0;
 }
-
-}  // namespace
+int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h,
+                  uint32_t box_w, uint32_t box_c) {
+    EncodeTiledFn enc = get_encode();
+    LG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[4] = {C, W, H, B};
+    cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed (%d) B=%llu H=%llu W=%llu C=%llu box=%ux%ux%u", (int)r,
+               (unsigned long long)B, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C, box_h, box_w, box_c);
+    return 0;
+}
+}  // namespace tma
 
 // Plan: number of k-slices so that (N/128) * ksplit approaches the SM count, with >= 2 k-blocks per slice.
 int gemm_tc_ksplit(int M, int N, int K) {
@@ -272,13 +255,15 @@ int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int 
     if (ksplit_out) *ksplit_out = ks;
 
     CUtensorMap mwa, mwb, mx;
-    LG_TRY(make_map(&mwa, Wa, (uint64_t)std::min(n_split, N), (uint64_t)K, (uint64_t)K, kBlockN));
-    LG_TRY(make_map(&mwb, Wb, (uint64_t)std::max(N - n_split, Wb == Wa ? N : 1), (uint64_t)K, (uint64_t)K, kBlockN));
-    LG_TRY(make_map(&mx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, (uint32_t)a.rpad));
+    LG_TRY(tma::make_map_2d(&mwa, Wa, (uint64_t)std::min(n_split, N), (uint64_t)K, (uint64_t)K, kBlockN, kBlockK));
+    LG_TRY(tma::make_map_2d(&mwb, Wb, (uint64_t)std::max(N - n_split, Wb == Wa ? N : 1), (uint64_t)K, (uint64_t)K, kBlockN, kBlockK));
+    LG_TRY(tma::make_map_2d(&mx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, (uint32_t)a.rpad, kBlockK));
 
     const int b_tile_bytes = a.rpad * kBlockK * 2;
     const int stage_bytes = kATileBytes + ((b_tile_bytes + 1023) / 1024) * 1024;
-    const size_t smem = 1024 + (size_t)kStages * stage_bytes + (2 * kStages + 1) * sizeof(uint64_t) + 16;
+    a.stages = std::min(kMaxStages, (int)((225 * 1024 - 1024) / stage_bytes));
+    LG_REQUIRE(a.stages >= 2, "gemm_tc: tile too large for a 2-stage ring");
+    const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
     static bool attr = false;
     if (!attr) {
         LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -92,8 +92,21 @@ struct AttnArgs {
     int B, Tc;
     float scale;
     int dtype;
+    // TMA path (attn_tma.cu): tensor maps over the whole K / V cache regions + this layer's first row
+    const void* kmap = nullptr; const void* vmap = nullptr;
+    long long cache_row_base = 0;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
+// attn_tma.cu — TMA + tensor-core decode attention for bf16 caches
+int attn_tma_make_map(void* map_out /*CUtensorMap, 128 B*/, const void* cache_base, long long total_rows, int hd);
+bool attn_tma_supported(const AttnArgs& a);
+int launch_attention_tma(const AttnArgs& a, cudaStream_t st);
+// gemm_tc.cu — tcgen05/TMEM/TMA weight-streaming GEMM (bf16, M <= 256)
+int gemm_tc_ksplit(int M, int N, int K);
+bool gemm_tc_supported(int M, int N, int K, int dtype);
+int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
+                    float* partial, int* ksplit_out, cudaStream_t st);
+int lg_env_flag(const char* name, int dflt);
 
 // *pos += 1; *step += 1  (device-side loop counters for graph replay)
 int launch_advance(int* pos, int* step, cudaStream_t st);

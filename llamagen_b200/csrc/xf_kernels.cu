@@ -6,6 +6,7 @@
 // TransformerBlock.forward :253-257.  Every value the reference materialises as a tensor in the
 // model dtype T is rounded to T at the same point here (ElemTraits<T>::round).
 #include "kernels.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -67,8 +68,30 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, c
 }
 
 // ---------------------------------------------------------------- QKV epilogue: RoPE + cache write
+__device__ __forceinline__ float4 sum_partials4(const float* __restrict__ p, size_t idx, int ks, size_t slab) {
+    float4 s = *reinterpret_cast<const float4*>(p + idx);
+    for (int k = 1; k < ks; ++k) {
+        const float4 t = *reinterpret_cast<const float4*>(p + idx + (size_t)k * slab);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    return s;
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+template <typename T> __device__ __forceinline__ void load4(const T* p, float* o) { VecLoad<T, 4>::load(p, o); }
+
+// One CTA per row, one thread per 4 consecutive output features (two RoPE pairs), all loads up front.
 template <typename T>
-__global__ void __launch_bounds__(256) qkv_epilogue_kernel(QkvEpiArgs a) {
+__global__ void __launch_bounds__(1024) qkv_epilogue_kernel(QkvEpiArgs a) {
     const int m = blockIdx.x, r = m / a.Tq, t = m % a.Tq;
     const int p = load_pos(a.pos) + t;
     const int D = a.D, hd = a.hd, half = hd >> 1, N = 3 * D;
@@ -77,69 +100,75 @@ __global__ void __launch_bounds__(256) qkv_epilogue_kernel(QkvEpiArgs a) {
     T* q = reinterpret_cast<T*>(a.q);
     T* kc = reinterpret_cast<T*>(a.kcache);
     T* vc = reinterpret_cast<T*>(a.vcache);
-    for (int i = threadIdx.x; i < N / 2; i += blockDim.x) {
-        const int n = 2 * i;
-        const size_t idx = (size_t)m * N + n;
+    for (int n = threadIdx.x * 4; n < N; n += blockDim.x * 4) {
+        const float4 sv = sum_partials4(a.partial, (size_t)m * N + n, a.ksplit, slab);
         // the GEMM output is a T tensor in the reference; RoPE then runs in fp32 (gpt.py:423)
-        const float x0 = TR<T>::round(sum_partials(a.partial, idx, a.ksplit, slab));
-        const float x1 = TR<T>::round(sum_partials(a.partial, idx + 1, a.ksplit, slab));
-        const int sec = n / D, within = n - sec * D, head = within / hd, e = within - head * hd;
+        const float x0 = TR<T>::round(sv.x), x1 = TR<T>::round(sv.y), x2 = TR<T>::round(sv.z), x3 = TR<T>::round(sv.w);
+        const int sec = n / D, within = n - sec * D, head = within / hd, e = within - head * hd;   // hd % 4 == 0
         if (sec == 2) {
-            const size_t o = (((size_t)r * a.H + head) * a.maxS + p) * hd + e;
-            vc[o] = TR<T>::from_f(x0);
-            vc[o + 1] = TR<T>::from_f(x1);
+            store4<T>(vc + (((size_t)r * a.H + head) * a.maxS + p) * hd + e, x0, x1, x2, x3);
         } else {
-            const float c = fr[(e >> 1) * 2], s = fr[(e >> 1) * 2 + 1];
-            const float y0 = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
-            const float y1 = __fadd_rn(__fmul_rn(x1, c), __fmul_rn(x0, s));
-            if (sec == 0) {
-                q[(size_t)m * D + within] = TR<T>::from_f(y0);
-                q[(size_t)m * D + within + 1] = TR<T>::from_f(y1);
-            } else {
-                const size_t o = (((size_t)r * a.H + head) * a.maxS + p) * hd + e;
-                kc[o] = TR<T>::from_f(y0);
-                kc[o + 1] = TR<T>::from_f(y1);
-            }
+            const float4 cs = *reinterpret_cast<const float4*>(fr + (e >> 1) * 2);   // (cos, sin) of two pairs
+            const float y0 = __fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y));
+            const float y1 = __fadd_rn(__fmul_rn(x1, cs.x), __fmul_rn(x0, cs.y));
+            const float y2 = __fsub_rn(__fmul_rn(x2, cs.z), __fmul_rn(x3, cs.w));
+            const float y3 = __fadd_rn(__fmul_rn(x3, cs.z), __fmul_rn(x2, cs.w));
+            T* dst = sec == 0 ? q + (size_t)m * D + within : kc + (((size_t)r * a.H + head) * a.maxS + p) * hd + e;
+            store4<T>(dst, y0, y1, y2, y3);
         }
     }
 }
 
 // ---------------------------------------------------------------- residual add (+ next RMSNorm)
+// One CTA per row, D/4 threads, everything in registers between the two phases (D <= 4096).
 template <typename T>
-__global__ void __launch_bounds__(256) residual_norm_kernel(const float* __restrict__ partial, int ks, int M,
-                                                            int D, T* __restrict__ h, const T* __restrict__ nw,
-                                                            T* __restrict__ xn, float eps) {
-    extern __shared__ float rowbuf[];  // D floats
+__global__ void __launch_bounds__(1024) residual_norm_kernel(const float* __restrict__ partial, int ks, int M,
+                                                             int D, T* __restrict__ h, const T* __restrict__ nw,
+                                                             T* __restrict__ xn, float eps) {
     __shared__ float red[33];
-    const int m = blockIdx.x;
+    const int m = blockIdx.x, i = threadIdx.x * 4;
     const size_t slab = (size_t)M * D, row = (size_t)m * D;
-    float ss = 0.f;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-        const float o = TR<T>::round(sum_partials(partial, row + i, ks, slab));
-        const float v = TR<T>::round(TR<T>::to_f(h[row + i]) + o);  // h = x + f(x) in dtype T (gpt.py:255-256)
-        h[row + i] = TR<T>::from_f(v);
-        rowbuf[i] = v;
-        ss += v * v;
+    float v[4] = {0.f, 0.f, 0.f, 0.f}, w[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool act = i < D;
+    if (act) {
+        const float4 o = sum_partials4(partial, row + i, ks, slab);
+        float hv[4];
+        load4<T>(h + row + i, hv);
+        if (xn) load4<T>(nw + i, w);
+        // h = x + f(x) in dtype T (gpt.py:255-256): the branch output is a T tensor, the sum is rounded again
+        v[0] = TR<T>::round(hv[0] + TR<T>::round(o.x));
+        v[1] = TR<T>::round(hv[1] + TR<T>::round(o.y));
+        v[2] = TR<T>::round(hv[2] + TR<T>::round(o.z));
+        v[3] = TR<T>::round(hv[3] + TR<T>::round(o.w));
+        store4<T>(h + row + i, v[0], v[1], v[2], v[3]);
     }
     if (xn == nullptr) return;
+    float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
     ss = block_sum(ss, red);
     const float r = 1.0f / sqrtf(ss / (float)D + eps);
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-        const float v = TR<T>::round(rowbuf[i] * r);
-        xn[row + i] = TR<T>::from_f(v * TR<T>::to_f(nw[i]));
-    }
+    if (act)
+        store4<T>(xn + row + i, TR<T>::round(v[0] * r) * w[0], TR<T>::round(v[1] * r) * w[1],
+                  TR<T>::round(v[2] * r) * w[2], TR<T>::round(v[3] * r) * w[3]);
 }
 
 // ---------------------------------------------------------------- SwiGLU gate (gpt.py:167)
 template <typename T>
 __global__ void silu_mul_kernel(const float* __restrict__ partial, int ks, int M, int F, T* __restrict__ out) {
-    const size_t total = (size_t)M * F, slab = (size_t)M * 2 * F;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t m = i / F, j = i - m * F;
-        const float a = TR<T>::round(sum_partials(partial, m * 2 * F + j, ks, slab));
-        const float b = TR<T>::round(sum_partials(partial, m * 2 * F + F + j, ks, slab));
-        const float s = TR<T>::round(a / (1.0f + expf(-a)));
-        out[i] = TR<T>::from_f(s * b);
+    const size_t total4 = (size_t)M * F / 4, slab = (size_t)M * 2 * F;
+    const int f4 = F / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t m = i / f4, j = (i - m * f4) * 4;
+        const float4 a4 = sum_partials4(partial, m * 2 * F + j, ks, slab);
+        const float4 b4 = sum_partials4(partial, m * 2 * F + F + j, ks, slab);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float av = TR<T>::round(a[k]), bv = TR<T>::round(b[k]);
+            const float sv = TR<T>::round(av / (1.0f + expf(-av)));
+            o[k] = sv * bv;
+        }
+        store4<T>(out + m * F + j, o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -321,25 +350,27 @@ int launch_rmsnorm(const void* x, const void* w, void* xn, int M, int D, float e
 }
 
 int launch_qkv_epilogue(const QkvEpiArgs& a, cudaStream_t st) {
-    LG_REQUIRE(a.hd % 2 == 0, "head_dim %d must be even for RoPE pairs", a.hd);
+    LG_REQUIRE(a.hd % 4 == 0 && a.D % 4 == 0, "head_dim %d / dim %d must be multiples of 4", a.hd, a.D);
+    const int threads = std::min(1024, ((3 * a.D / 4 + 31) / 32) * 32);
     return dispatch_dtype(
         a.dtype,
-        [&] { qkv_epilogue_kernel<float><<<a.M, 256, 0, st>>>(a); LG_LAUNCH_CHECK(); return 0; },
-        [&] { qkv_epilogue_kernel<bf16><<<a.M, 256, 0, st>>>(a); LG_LAUNCH_CHECK(); return 0; });
+        [&] { qkv_epilogue_kernel<float><<<a.M, threads, 0, st>>>(a); LG_LAUNCH_CHECK(); return 0; },
+        [&] { qkv_epilogue_kernel<bf16><<<a.M, threads, 0, st>>>(a); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_residual_norm(const float* partial, int ksplit, int M, int D, void* h, const void* norm_w, void* xn,
                          float eps, int dtype, cudaStream_t st) {
-    const size_t smem = (size_t)D * sizeof(float);
-    LG_REQUIRE(smem <= 48 * 1024, "dim %d too large for the residual row stage", D);
+    LG_REQUIRE(D % 4 == 0 && D <= 4096, "dim %d must be a multiple of 4 and <= 4096", D);
+    const int threads = ((D / 4 + 31) / 32) * 32;
     return dispatch_dtype(
         dtype,
-        [&] { residual_norm_kernel<float><<<M, 256, smem, st>>>(partial, ksplit, M, D, (float*)h, (const float*)norm_w, (float*)xn, eps); LG_LAUNCH_CHECK(); return 0; },
-        [&] { residual_norm_kernel<bf16><<<M, 256, smem, st>>>(partial, ksplit, M, D, (bf16*)h, (const bf16*)norm_w, (bf16*)xn, eps); LG_LAUNCH_CHECK(); return 0; });
+        [&] { residual_norm_kernel<float><<<M, threads, 0, st>>>(partial, ksplit, M, D, (float*)h, (const float*)norm_w, (float*)xn, eps); LG_LAUNCH_CHECK(); return 0; },
+        [&] { residual_norm_kernel<bf16><<<M, threads, 0, st>>>(partial, ksplit, M, D, (bf16*)h, (const bf16*)norm_w, (bf16*)xn, eps); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_silu_mul(const float* partial, int ksplit, int M, int F, void* out, int dtype, cudaStream_t st) {
-    const int blocks = (int)std::min<long long>(((long long)M * F + 255) / 256, 148 * 16);
+    LG_REQUIRE(F % 4 == 0, "ffn dim %d must be a multiple of 4", F);
+    const int blocks = (int)std::min<long long>(((long long)M * F / 4 + 255) / 256, 148 * 16);
     return dispatch_dtype(
         dtype,
         [&] { silu_mul_kernel<float><<<blocks, 256, 0, st>>>(partial, ksplit, M, F, (float*)out); LG_LAUNCH_CHECK(); return 0; },
@@ -375,6 +406,7 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t st) {
 }
 
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
+    if (attn_tma_supported(a) && lg_env_flag("LG_ATTN_TMA", 1)) return launch_attention_tma(a, st);
     LG_REQUIRE((long long)a.R * a.Tq <= 65535, "attention: too many query rows (%d x %d)", a.R, a.Tq);
     if (a.dtype == LG_DTYPE_BF16) {
         if (a.hd == 64) return launch_attention_t<bf16, 64, 8, 8>(a, st);
