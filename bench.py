@@ -153,6 +153,45 @@ def algorithmic(name, R, S, T=1, V=16384):
     return dict(step_bytes=step_bytes, step_flops=step_flops, per_launch=per_launch, per_launch_flops=per_launch_flops)
 
 
+def kernel_class(name: str) -> str:
+    n = name.replace("(anonymous namespace)::", "")
+    if "attn_tma" in n or "attention_kernel" in n:
+        return "attention"
+    if "ConvA" in n:
+        return "vq_conv_gemm"
+    if "EpiVq" in n or "softmax_rows" in n:
+        return "vq_attn"
+    if "gemm_tc_kernel" in n or "gemm_skinny" in n or "gemm_mma_kernel" in n:
+        return "dense_gemm"
+    for key, cls in (("residual_norm", "residual_rmsnorm"), ("qkv_epilogue", "qkv_rope_kvwrite"), ("silu_mul", "silu_mul"),
+                     ("sample_kernel", "sample"), ("gn_stats", "vq_gn_stats"), ("gn_apply", "vq_gn_apply"),
+                     ("lookup_postquant", "vq_misc")):
+        if key in n:
+            return cls
+    return "embed_misc"
+
+
+def trace_classes(fn, dev):
+    """Per-kernel-class device time of one call of fn(), from CUPTI kernel records (device timestamps)."""
+    try:
+        import torch
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize(dev)
+        out = {}
+        for e in prof.events():
+            if e.device_type != torch.autograd.DeviceType.CUDA:
+                continue
+            c = out.setdefault(kernel_class(e.name), {"total_ms": 0.0, "launches": 0})
+            c["total_ms"] += (e.time_range.end - e.time_range.start) / 1000.0
+            c["launches"] += 1
+        return out if out else None
+    except Exception as ex:      # pragma: no cover
+        log(f"CUPTI trace unavailable: {ex}")
+        return None
+
+
 VQ_GFLOP_PER_IMAGE = {16: 252.7, 24: 570.1, 32: 1017.3}   # SURVEY §8a-7 (conv-hook count on the reference)
 
 
@@ -329,50 +368,75 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(host_pixels.numel()), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks}
 
-    # ---------------- roofline leg: per-kernel-class CUDA-event timing of one extra (untimed) step, rank 0 only
+    # ---------------- roofline leg: device-side kernel durations (CUPTI via torch.profiler) of one extra step, rank 0
     if rank == 0 and not args.no_roofline:
         pk = peaks()
-        log("roofline leg: profiling one step per kernel class")
-        lib.lg_profile_reset()
-        lib.lg_profile_enable(1)
-        step_resident(labels_dev)
-        torch.cuda.synchronize()
-        lib.lg_profile_enable(0)
-        classes, i = {}, 0
-        while True:
-            nm = lib.lg_profile_class_name(i)
-            if nm is None:
-                break
-            t, n = ctypes.c_double(), ctypes.c_uint64()
-            lib.lg_profile_read(i, ctypes.byref(t), ctypes.byref(n))
-            if n.value:
-                classes[nm.decode()] = {"total_ms": t.value, "launches": int(n.value), "avg_us": 1000.0 * t.value / n.value}
-            i += 1
+        log("roofline leg: tracing one step (CUPTI kernel timestamps)")
+        classes = trace_classes(lambda: step_resident(labels_dev), dev)
+        if classes is None:      # CUPTI unavailable: event-bracketed launches through the library's own profiler
+            lib.lg_profile_reset()
+            lib.lg_profile_enable(1)
+            step_resident(labels_dev)
+            torch.cuda.synchronize()
+            lib.lg_profile_enable(0)
+            classes, i = {}, 0
+            while True:
+                nm = lib.lg_profile_class_name(i)
+                if nm is None:
+                    break
+                t, n = ctypes.c_double(), ctypes.c_uint64()
+                lib.lg_profile_read(i, ctypes.byref(t), ctypes.byref(n))
+                if n.value:
+                    key = nm.decode()
+                    key = "dense_gemm" if key.startswith("gemm_") else key
+                    c = classes.setdefault(key, {"total_ms": 0.0, "launches": 0})
+                    c["total_ms"] += t.value
+                    c["launches"] += int(n.value)
+            timing_source = "cudaEvent pairs around eager launches (includes launch latency)"
+        else:
+            timing_source = "CUPTI kernel timestamps inside the CUDA-graph replay (torch.profiler)"
         alg = algorithmic(args.gpt_model, R, S)
-        dom = max((k for k in classes if k in alg["per_launch"]), key=lambda k: classes[k]["total_ms"], default=None)
+        L = model_dims(args.gpt_model)[0]
+        # algorithmic work of one whole step (S tokens, B images) per kernel class
+        work = {
+            "attention": {"bytes": alg["per_launch"]["attention"] * L * S, "flops": alg["per_launch_flops"]["attention"] * L * S, "bound": "hbm"},
+            "dense_gemm": {"bytes": sum(alg["per_launch"][k] for k in ("gemm_qkv", "gemm_wo", "gemm_w13", "gemm_w2")) * L * S + alg["per_launch"]["gemm_head"] * S,
+                           "flops": sum(alg["per_launch_flops"][k] for k in ("gemm_qkv", "gemm_wo", "gemm_w13", "gemm_w2")) * L * S + alg["per_launch_flops"]["gemm_head"] * S,
+                           "bound": "hbm"},
+            "vq_conv_gemm": {"bytes": None, "flops": B * VQ_GFLOP_PER_IMAGE.get(g, 0.0) * 1e9, "bound": "tensor"},
+        }
+        total_ms = sum(v["total_ms"] for v in classes.values())
+        line["kernels"] = {}
+        for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["total_ms"]):
+            e = {"total_ms": round(v["total_ms"], 3), "launches": v["launches"], "avg_us": round(1000.0 * v["total_ms"] / v["launches"], 2),
+                 "share": round(v["total_ms"] / total_ms, 4)}
+            if k in work:
+                if work[k]["bytes"]:
+                    e["hbm_gbs"] = round(work[k]["bytes"] / (v["total_ms"] * 1e-3) / 1e9, 1)
+                e["tflops"] = round(work[k]["flops"] / (v["total_ms"] * 1e-3) / 1e12, 1)
+            line["kernels"][k] = e
+        dom = max((k for k in classes if k in work), key=lambda k: classes[k]["total_ms"], default=None)
         if dom:
-            avg_s = classes[dom]["avg_us"] * 1e-6
-            ach = alg["per_launch"][dom] / avg_s / 1e9
-            line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                                "algorithmic_bytes_per_launch": alg["per_launch"][dom], "avg_launch_us": classes[dom]["avg_us"]}
-        total_ar = sum(v["total_ms"] for k, v in classes.items() if not k.startswith("vq_"))
-        total_vq = sum(v["total_ms"] for k, v in classes.items() if k.startswith("vq_"))
+            v = classes[dom]
+            if work[dom]["bound"] == "hbm":
+                ach = work[dom]["bytes"] / (v["total_ms"] * 1e-3) / 1e9
+                line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                                    "algorithmic_bytes_per_launch": work[dom]["bytes"] / v["launches"],
+                                    "avg_launch_us": 1000.0 * v["total_ms"] / v["launches"], "timing": timing_source}
+            else:
+                ach = work[dom]["flops"] / (v["total_ms"] * 1e-3) / 1e12
+                line["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                                    "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"],
+                                    "algorithmic_flops_per_launch": work[dom]["flops"] / v["launches"],
+                                    "avg_launch_us": 1000.0 * v["total_ms"] / v["launches"], "timing": timing_source}
         step_roof_ms = 1000.0 * max(alg["step_bytes"] / (pk["hbm_gbs"] * 1e9), alg["step_flops"] / (pk["bf16_sustained"] * 1e12))
         vq_roof_ms = B * VQ_GFLOP_PER_IMAGE.get(g, 0.0) / (pk["bf16_sustained"] * 1e3) * 1e3
-        line["kernels"] = {k: {"avg_us": round(v["avg_us"], 2), "launches": v["launches"], "share": round(v["total_ms"] / (total_ar + total_vq), 4)}
-                           for k, v in classes.items()}
-        for k in classes:
-            if k in alg["per_launch"]:
-                s = classes[k]["avg_us"] * 1e-6
-                line["kernels"][k]["hbm_gbs"] = round(alg["per_launch"][k] / s / 1e9, 1)
-                line["kernels"][k]["tflops"] = round(alg["per_launch_flops"][k] / s / 1e12, 1)
-        if "vq_conv_gemm" in classes:
-            line["kernels"]["vq_conv_gemm"]["tflops"] = round(B * VQ_GFLOP_PER_IMAGE.get(g, 0.0) / classes["vq_conv_gemm"]["total_ms"], 1)
+        total_vq = sum(v["total_ms"] for k, v in classes.items() if k.startswith("vq_"))
         line["step_roofline"] = {"decode_step_floor_us": round(step_roof_ms * 1000, 1), "ar_floor_ms": round(step_roof_ms * S, 2),
                                  "vq_floor_ms": round(vq_roof_ms, 2), "measured_ms_per_step": round(ms / args.steps, 2),
                                  "frac_of_floor": round((step_roof_ms * S + vq_roof_ms) / (ms / args.steps), 4),
-                                 "profiled_ar_ms": round(total_ar, 2), "profiled_vq_ms": round(total_vq, 2)}
+                                 "traced_ar_kernel_ms": round(total_ms - total_vq, 2), "traced_vq_kernel_ms": round(total_vq, 2)}
 
     # ---------------- CPU baseline leg (rank 0, N=1 only): bounded sample of the same workload on the host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -61,6 +61,38 @@ bool lg_debug_sync();
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel of the decode step is launched with
+// programmaticStreamSerializationAllowed so its CTAs are scheduled (and run their prologue) while the
+// previous kernel drains; lg_pdl_sync() at the top of the kernel blocks until the producer grid's memory
+// is visible. Inside the captured CUDA graph these become programmatic dependency edges.
+// ---------------------------------------------------------------------------------------------
+int lg_env_flag(const char* name, int dflt);
+inline bool lg_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) v = lg_env_flag("LG_PDL", 1) ? 1 : 0;
+    return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t lg_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = lg_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void lg_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void lg_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void lg_pdl_sync() { lg_pdl_wait(); lg_pdl_launch_dependents(); }
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // element conversion. The reference keeps activations in the weight dtype, so every op output is
 // rounded to T (bf16 RNE) exactly where torch would materialise a tensor.
 // ---------------------------------------------------------------------------------------------

@@ -579,13 +579,14 @@ int lg_test_gemm(const void* x, const void* w, int M, int N, int K, int dtype, f
 
 namespace {
 __global__ void round_bf16_kernel(float* p, size_t n) {
+    lg_pdl_sync();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         p[i] = round_bf16(p[i]);
 }
 }  // namespace
 static int round_logits_inplace(float* logits, size_t n, cudaStream_t st) {
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
-    round_bf16_kernel<<<blocks, 256, 0, st>>>(logits, n);
+    (void)lg_launch(round_bf16_kernel, dim3(blocks), dim3(256), 0, st, logits, n);
     LG_LAUNCH_CHECK();
     return 0;
 }

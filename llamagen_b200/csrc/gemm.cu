@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(kSkinnyWarps * 32) gemm_skinny_kernel(const T*
                                                                         const T* __restrict__ Wb, int n_split,
                                                                         int M, int N, int K, int kper,
                                                                         float* __restrict__ partial) {
+    lg_pdl_sync();
     constexpr int VEC = 16 / sizeof(T);
     constexpr int RT = kSkinnyRT, KC = kSkinnyKC;
     extern __shared__ __align__(16) unsigned char sraw[];
@@ -144,11 +145,11 @@ int gemm_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_s
                 LG_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 attr = true;
             }
-            gemm_skinny_kernel<float><<<grid, kSkinnyWarps * 32, smem, st>>>(
+            (void)lg_launch(gemm_skinny_kernel<float>, dim3(grid), dim3(kSkinnyWarps * 32), smem, st, 
                 (const float*)X, ldx, (const float*)Wa, (const float*)Wb, n_split, M, N, K, kper, partial);
         } else {
             const size_t smem = (size_t)kSkinnyRT * kSkinnyKC * sizeof(bf16);
-            gemm_skinny_kernel<bf16><<<grid, kSkinnyWarps * 32, smem, st>>>(
+            (void)lg_launch(gemm_skinny_kernel<bf16>, dim3(grid), dim3(kSkinnyWarps * 32), smem, st, 
                 (const bf16*)X, ldx, (const bf16*)Wa, (const bf16*)Wb, n_split, M, N, K, kper, partial);
         }
         LG_LAUNCH_CHECK();

@@ -110,6 +110,7 @@ struct EpiPartial {          // fp32 slabs [z][M][N]
 template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, class AL, class Epi>
 __global__ void __launch_bounds__(kThreads) gemm_mma_kernel(AL al, BRows bw, int M, int N, int K, int kper,
                                                             int ksplit, Epi epi) {
+    lg_pdl_sync();
     static_assert(WARPS_M * WARPS_N == 8, "8 warps");
     constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;
     constexpr int MT = WTM / 16, NT = WTN / 8;
@@ -232,7 +233,7 @@ int launch_gemm_mma(const AL& al, const BRows& bw, int M, int N, int K, int kspl
     const int kper = ((kt_total + ksplit - 1) / ksplit) * BK;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, nbatch * ksplit);
     LG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm: grid too large (%u, %u)", grid.y, grid.z);
-    kern<<<grid, kThreads, smem, st>>>(al, bw, M, N, K, kper, ksplit, epi);
+    (void)lg_launch(kern, grid, dim3(kThreads), smem, st, al, bw, M, N, K, kper, ksplit, epi);
     LG_LAUNCH_CHECK();
     return 0;
 }

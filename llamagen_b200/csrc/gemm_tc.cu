@@ -9,8 +9,11 @@
 // HBM exactly once. One CTA = one (n-tile, k-slice); split-K slabs (fp32) are reduced by the row-wise
 // epilogue kernels in xf_kernels.cu, exactly like the mma.sync path it replaces (gemm.cu).
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected
-// lane) + TMEM allocator, warps 2..5 = epilogue (each owns the TMEM lane quarter (warp % 4)).
+// Warp roles (256 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane)
+// + TMEM allocator; when the accumulator is complete all 8 warps drain it (TMEM lane quarter = warp % 4,
+// column half = warp / 4). The drain is written as a pointer walk (one IADD + one STG per value): a lone warp per
+// scheduler is latency-bound, so every instruction in this loop costs ~4 cycles (measured: the first version
+// spent 4.8 us of a 7 us kernel here).
 #include "kernels.cuh"
 #include "tma_utils.cuh"
 #include <mutex>
@@ -21,7 +24,7 @@ namespace {
 constexpr int kBlockN = 128;    // weight rows per CTA  (UMMA M)
 constexpr int kBlockK = 64;     // bf16 elements per k-block = 128 B = one swizzle-128B row
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;   // 8 warps: TMA producer, MMA issuer, then ALL of them drain the accumulator
 constexpr int kATileBytes = kBlockN * kBlockK * 2;   // 16 KB
 
 using namespace tma;
@@ -70,7 +73,18 @@ struct TcArgs {
     int tmem_cols;        // power of two >= max(32, rpad)
     int stages;           // smem ring depth (<= kMaxStages), sized to fit 227 KB
     float* partial;       // [ksplit][M][N]
+    unsigned long long* trace;   // debug: [cta][8] %globaltimer stamps of the pipeline phases (nullable)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC_TRACE(slot)                                                                            \
+    do {                                                                                          \
+        if (a.trace) a.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); \
+    } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_wa,
                                                               const __grid_constant__ CUtensorMap map_wb,
@@ -89,6 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * kBlockN;
     const int ks = blockIdx.y;
+    if (threadIdx.x == 0) TC_TRACE(0);
     const int total_kb = (a.K + kBlockK - 1) / kBlockK;
     const int kb0 = ks * a.kblocks_per_split;
     const int nkb = max(0, min(a.kblocks_per_split, total_kb - kb0));
@@ -106,6 +121,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_slot;
+    if (threadIdx.x == 0) TC_TRACE(1);
+    lg_pdl_launch_dependents();
+    if (warp != 0) lg_pdl_wait();   // warp 0 waits after it has requested the first weight tiles
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -114,7 +132,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const CUtensorMap* wmap = second ? &map_wb : &map_wa;
             const int wrow = second ? n0 - a.n_split : n0;
             const uint32_t tx = (uint32_t)(kATileBytes + b_tile_bytes);
-            for (int i = 0; i < nkb; ++i) {
+            // Weights do not depend on the previous kernel: the first ring of weight tiles is requested BEFORE
+            // the programmatic-dependency wait, so the HBM stream of this GEMM overlaps the tail of its producer.
+            const int npre = min(nkb, kStages);
+            for (int i = 0; i < npre; ++i) {
+                mbar_expect_tx(&full_bar[i], tx);
+                load_2d(tiles + i * stage_bytes, wmap, &full_bar[i], (kb0 + i) * kBlockK, wrow);
+            }
+            lg_pdl_wait();
+            for (int i = 0; i < npre; ++i)
+                load_2d(tiles + i * stage_bytes + kATileBytes, &map_x, &full_bar[i], (kb0 + i) * kBlockK, 0);
+            for (int i = npre; i < nkb; ++i) {
                 const int s = i % kStages;
                 const uint32_t ph = (uint32_t)((i / kStages) & 1);
                 mbar_wait(&empty_bar[s], ph ^ 1);
@@ -123,7 +151,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 load_2d(sa, wmap, &full_bar[s], (kb0 + i) * kBlockK, wrow);
                 load_2d(sa + kATileBytes, &map_x, &full_bar[s], (kb0 + i) * kBlockK, 0);
             }
+            TC_TRACE(2);
         }
+        __syncwarp();      // reconverge: the drain below uses warp-collective (.sync.aligned) TMEM loads
+        lg_pdl_wait();
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = make_idesc(a.rpad);
@@ -132,6 +163,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const uint32_t ph = (uint32_t)((i / kStages) & 1);
             mbar_wait(&full_bar[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (i == 0 && lane == 0) TC_TRACE(3);
+            if (i == nkb - 1 && lane == 0) TC_TRACE(4);
             if (elect_one()) {
                 const uint32_t sa = smem_u32(tiles + s * stage_bytes);
                 const uint64_t adesc = make_desc_sw128(sa);
@@ -146,30 +179,46 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
             __syncwarp();
         }
-    } else {
-        // ------------------------------------------------------------------ epilogue: TMEM -> registers -> fp32 slab
+    }
+    // ---------------------------------------------------------------------- drain: TMEM -> registers -> fp32 slab
+    {
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = warp >> 2;                   // which half of the columns (activation rows) it drains
         const int n = n0 + q * 32 + lane;
+        const int cols_half = ((a.rpad / 16 + 1) / 2) * 16;
+        const int c_begin = half * cols_half, c_end = min(a.rpad, c_begin + cols_half);
         float* out = a.partial + (size_t)ks * a.M * a.N;
         if (nkb > 0) {
             mbar_wait(tmem_full_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int c0 = 0; c0 < a.rpad; c0 += 16) {
+            if (threadIdx.x == 64) TC_TRACE(5);
+            float* p = out + (size_t)c_begin * a.N + n;
+            const size_t stride = (size_t)a.N;
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 if (n < a.N) {
+                    if (c0 + 16 <= a.M) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < a.M) out[(size_t)(c0 + j) * a.N + n] = __uint_as_float(v[j]);
+                        for (int j = 0; j < 16; ++j) { *p = __uint_as_float(v[j]); p += stride; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (c0 + j < a.M) *p = __uint_as_float(v[j]);
+                            p += stride;
+                        }
+                    }
                 }
             }
         } else if (n < a.N) {
-            for (int r = 0; r < a.M; ++r) out[(size_t)r * a.N + n] = 0.f;
+            for (int r = c_begin; r < min(c_end, a.M); ++r) out[(size_t)r * a.N + n] = 0.f;
         }
     }
+    if (threadIdx.x == 64) TC_TRACE(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    if (threadIdx.x == 0) TC_TRACE(7);
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -223,6 +272,9 @@ int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t B, uint64_t H, uint
 }
 }  // namespace tma
 
+static unsigned long long* g_tc_trace = nullptr;
+extern "C" void lg_debug_set_tc_trace(unsigned long long* dev_buf) { g_tc_trace = dev_buf; }
+
 // Plan: number of k-slices so that (N/128) * ksplit approaches the SM count, with >= 2 k-blocks per slice.
 int gemm_tc_ksplit(int M, int N, int K) {
     (void)M;
@@ -261,7 +313,9 @@ int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int 
 
     const int b_tile_bytes = a.rpad * kBlockK * 2;
     const int stage_bytes = kATileBytes + ((b_tile_bytes + 1023) / 1024) * 1024;
-    a.stages = std::min(kMaxStages, (int)((225 * 1024 - 1024) / stage_bytes));
+    a.stages = std::min(std::min(kMaxStages, lg_env_flag("LG_TC_STAGES", kMaxStages)), (int)((225 * 1024 - 1024) / stage_bytes));
+    a.stages = std::min(a.stages, std::max(2, a.kblocks_per_split));   // never more stages than k-blocks
+    a.trace = g_tc_trace;
     LG_REQUIRE(a.stages >= 2, "gemm_tc: tile too large for a 2-stage ring");
     const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
     static bool attr = false;
@@ -271,7 +325,7 @@ int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int 
     }
     LG_REQUIRE(smem <= 227 * 1024, "gemm_tc: shared memory %zu too large", smem);
     dim3 grid(cdiv(N, kBlockN), ks);
-    gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mwa, mwb, mx, a);
+    (void)lg_launch(gemm_tc_kernel, dim3(grid), dim3(kThreads), smem, st, mwa, mwb, mx, a);
     LG_LAUNCH_CHECK();
     return 0;
 }

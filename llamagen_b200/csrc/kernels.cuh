@@ -106,7 +106,6 @@ int gemm_tc_ksplit(int M, int N, int K);
 bool gemm_tc_supported(int M, int N, int K, int dtype);
 int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
                     float* partial, int* ksplit_out, cudaStream_t st);
-int lg_env_flag(const char* name, int dflt);
 
 // *pos += 1; *step += 1  (device-side loop counters for graph replay)
 int launch_advance(int* pos, int* step, cudaStream_t st);

@@ -31,6 +31,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 }
 
 __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
+    lg_pdl_sync();
     extern __shared__ float sh[];  // V floats: the working logits row, later exp() values
     __shared__ float red[33];
     __shared__ uint32_t hist[256];
@@ -326,7 +327,7 @@ int launch_sample(const SampleArgs& a, cudaStream_t st) {
         LG_CUDA_OK(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    sample_kernel<<<a.B, kSampleThreads, smem, st>>>(a);
+    (void)lg_launch(sample_kernel, dim3(a.B), dim3(kSampleThreads), smem, st, a);
     LG_LAUNCH_CHECK();
     return 0;
 }

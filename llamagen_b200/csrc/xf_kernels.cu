@@ -24,6 +24,7 @@ __device__ __forceinline__ float sum_partials(const float* __restrict__ p, size_
 template <typename T>
 __global__ void embed_kernel(const T* __restrict__ table, const int32_t* __restrict__ src, int B, int null_idx,
                              int D, T* __restrict__ out) {
+    lg_pdl_sync();
     const int r = blockIdx.x;
     const int idx = r < B ? src[r] : (null_idx >= 0 ? null_idx : src[r - B]);
     const T* s = table + (size_t)idx * D;
@@ -34,6 +35,7 @@ __global__ void embed_kernel(const T* __restrict__ table, const int32_t* __restr
 template <typename T>
 __global__ void caption_rows_kernel(const T* __restrict__ cond, const T* __restrict__ uncond, int B, int T_,
                                     int C, T* __restrict__ out) {
+    lg_pdl_sync();
     const int row = blockIdx.x, r = row / T_, t = row % T_;
     const T* s = r < B ? cond + ((size_t)r * T_ + t) * C : uncond + (size_t)t * C;
     T* d = out + (size_t)row * C;
@@ -42,6 +44,7 @@ __global__ void caption_rows_kernel(const T* __restrict__ cond, const T* __restr
 
 template <typename T>
 __global__ void gather_last_kernel(const T* __restrict__ in, int T_, int D, T* __restrict__ out) {
+    lg_pdl_sync();
     const int r = blockIdx.x;
     const T* s = in + ((size_t)r * T_ + (T_ - 1)) * D;
     T* d = out + (size_t)r * D;
@@ -52,6 +55,7 @@ __global__ void gather_last_kernel(const T* __restrict__ in, int T_, int D, T* _
 template <typename T>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w,
                                                       T* __restrict__ xn, int D, float eps) {
+    lg_pdl_sync();
     __shared__ float red[33];
     const size_t row = (size_t)blockIdx.x * D;
     float ss = 0.f;
@@ -92,6 +96,7 @@ template <typename T> __device__ __forceinline__ void load4(const T* p, float* o
 // One CTA per row, one thread per 4 consecutive output features (two RoPE pairs), all loads up front.
 template <typename T>
 __global__ void __launch_bounds__(1024) qkv_epilogue_kernel(QkvEpiArgs a) {
+    lg_pdl_sync();
     const int m = blockIdx.x, r = m / a.Tq, t = m % a.Tq;
     const int p = load_pos(a.pos) + t;
     const int D = a.D, hd = a.hd, half = hd >> 1, N = 3 * D;
@@ -125,6 +130,7 @@ template <typename T>
 __global__ void __launch_bounds__(1024) residual_norm_kernel(const float* __restrict__ partial, int ks, int M,
                                                              int D, T* __restrict__ h, const T* __restrict__ nw,
                                                              T* __restrict__ xn, float eps) {
+    lg_pdl_sync();
     __shared__ float red[33];
     const int m = blockIdx.x, i = threadIdx.x * 4;
     const size_t slab = (size_t)M * D, row = (size_t)m * D;
@@ -154,6 +160,7 @@ __global__ void __launch_bounds__(1024) residual_norm_kernel(const float* __rest
 // ---------------------------------------------------------------- SwiGLU gate (gpt.py:167)
 template <typename T>
 __global__ void silu_mul_kernel(const float* __restrict__ partial, int ks, int M, int F, T* __restrict__ out) {
+    lg_pdl_sync();
     const size_t total4 = (size_t)M * F / 4, slab = (size_t)M * 2 * F;
     const int f4 = F / 4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
@@ -175,6 +182,7 @@ __global__ void silu_mul_kernel(const float* __restrict__ partial, int ks, int M
 template <typename T>
 __global__ void store_act_kernel(const float* __restrict__ partial, int ks, size_t total, int gelu,
                                  T* __restrict__ out) {
+    lg_pdl_sync();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         float v = TR<T>::round(sum_partials(partial, i, ks, total));
         if (gelu) {  // nn.GELU(approximate='tanh'), gpt.py:122
@@ -187,6 +195,7 @@ __global__ void store_act_kernel(const float* __restrict__ partial, int ks, size
 }
 
 __global__ void reduce_f32_kernel(const float* __restrict__ partial, int ks, size_t total, float* __restrict__ out) {
+    lg_pdl_sync();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
         out[i] = sum_partials(partial, i, ks, total);
 }
@@ -198,6 +207,7 @@ __global__ void reduce_f32_kernel(const float* __restrict__ partial, int ks, siz
 // Mask (gpt.py:354 + generate.py:154-163): key j visible iff j <= qpos and (j >= Tc or emb_mask[r%B, j] != 0 or j == qpos).
 template <typename T, int HD, int VEC, int LPK>
 __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
+    lg_pdl_sync();
     constexpr int KPW = 32 / LPK;  // keys per warp per iteration
     constexpr int UNROLL = 4;
     extern __shared__ float smem[];  // [nwarps][HD + 2]
@@ -302,10 +312,12 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
 }
 
 __global__ void advance_kernel(int* pos, int* step) {
+    lg_pdl_sync();
     if (pos) *pos += 1;
     if (step) *step += 1;
 }
 __global__ void set_counters_kernel(int* pos, int pv, int* step, int sv) {
+    lg_pdl_sync();
     if (pos) *pos = pv;
     if (step) *step = sv;
 }
@@ -323,30 +335,30 @@ int launch_embed(const void* table, const int32_t* src, int B, int R, int null_i
                  cudaStream_t st) {
     return dispatch_dtype(
         dtype,
-        [&] { embed_kernel<float><<<R, 128, 0, st>>>((const float*)table, src, B, null_idx, D, (float*)out); LG_LAUNCH_CHECK(); return 0; },
-        [&] { embed_kernel<bf16><<<R, 128, 0, st>>>((const bf16*)table, src, B, null_idx, D, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
+        [&] { (void)lg_launch(embed_kernel<float>, dim3(R), dim3(128), 0, st, (const float*)table, src, B, null_idx, D, (float*)out); LG_LAUNCH_CHECK(); return 0; },
+        [&] { (void)lg_launch(embed_kernel<bf16>, dim3(R), dim3(128), 0, st, (const bf16*)table, src, B, null_idx, D, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_build_caption_rows(const void* cond, const void* uncond, int B, int R, int T, int C, int dtype, void* out,
                               cudaStream_t st) {
     return dispatch_dtype(
         dtype,
-        [&] { caption_rows_kernel<float><<<R * T, 128, 0, st>>>((const float*)cond, (const float*)uncond, B, T, C, (float*)out); LG_LAUNCH_CHECK(); return 0; },
-        [&] { caption_rows_kernel<bf16><<<R * T, 128, 0, st>>>((const bf16*)cond, (const bf16*)uncond, B, T, C, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
+        [&] { (void)lg_launch(caption_rows_kernel<float>, dim3(R * T), dim3(128), 0, st, (const float*)cond, (const float*)uncond, B, T, C, (float*)out); LG_LAUNCH_CHECK(); return 0; },
+        [&] { (void)lg_launch(caption_rows_kernel<bf16>, dim3(R * T), dim3(128), 0, st, (const bf16*)cond, (const bf16*)uncond, B, T, C, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_gather_last(const void* in, int R, int T, int D, int dtype, void* out, cudaStream_t st) {
     return dispatch_dtype(
         dtype,
-        [&] { gather_last_kernel<float><<<R, 128, 0, st>>>((const float*)in, T, D, (float*)out); LG_LAUNCH_CHECK(); return 0; },
-        [&] { gather_last_kernel<bf16><<<R, 128, 0, st>>>((const bf16*)in, T, D, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
+        [&] { (void)lg_launch(gather_last_kernel<float>, dim3(R), dim3(128), 0, st, (const float*)in, T, D, (float*)out); LG_LAUNCH_CHECK(); return 0; },
+        [&] { (void)lg_launch(gather_last_kernel<bf16>, dim3(R), dim3(128), 0, st, (const bf16*)in, T, D, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_rmsnorm(const void* x, const void* w, void* xn, int M, int D, float eps, int dtype, cudaStream_t st) {
     return dispatch_dtype(
         dtype,
-        [&] { rmsnorm_kernel<float><<<M, 256, 0, st>>>((const float*)x, (const float*)w, (float*)xn, D, eps); LG_LAUNCH_CHECK(); return 0; },
-        [&] { rmsnorm_kernel<bf16><<<M, 256, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)xn, D, eps); LG_LAUNCH_CHECK(); return 0; });
+        [&] { (void)lg_launch(rmsnorm_kernel<float>, dim3(M), dim3(256), 0, st, (const float*)x, (const float*)w, (float*)xn, D, eps); LG_LAUNCH_CHECK(); return 0; },
+        [&] { (void)lg_launch(rmsnorm_kernel<bf16>, dim3(M), dim3(256), 0, st, (const bf16*)x, (const bf16*)w, (bf16*)xn, D, eps); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_qkv_epilogue(const QkvEpiArgs& a, cudaStream_t st) {
@@ -354,8 +366,8 @@ int launch_qkv_epilogue(const QkvEpiArgs& a, cudaStream_t st) {
     const int threads = std::min(1024, ((3 * a.D / 4 + 31) / 32) * 32);
     return dispatch_dtype(
         a.dtype,
-        [&] { qkv_epilogue_kernel<float><<<a.M, threads, 0, st>>>(a); LG_LAUNCH_CHECK(); return 0; },
-        [&] { qkv_epilogue_kernel<bf16><<<a.M, threads, 0, st>>>(a); LG_LAUNCH_CHECK(); return 0; });
+        [&] { (void)lg_launch(qkv_epilogue_kernel<float>, dim3(a.M), dim3(threads), 0, st, a); LG_LAUNCH_CHECK(); return 0; },
+        [&] { (void)lg_launch(qkv_epilogue_kernel<bf16>, dim3(a.M), dim3(threads), 0, st, a); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_residual_norm(const float* partial, int ksplit, int M, int D, void* h, const void* norm_w, void* xn,
@@ -364,8 +376,8 @@ int launch_residual_norm(const float* partial, int ksplit, int M, int D, void* h
     const int threads = ((D / 4 + 31) / 32) * 32;
     return dispatch_dtype(
         dtype,
-        [&] { residual_norm_kernel<float><<<M, threads, 0, st>>>(partial, ksplit, M, D, (float*)h, (const float*)norm_w, (float*)xn, eps); LG_LAUNCH_CHECK(); return 0; },
-        [&] { residual_norm_kernel<bf16><<<M, threads, 0, st>>>(partial, ksplit, M, D, (bf16*)h, (const bf16*)norm_w, (bf16*)xn, eps); LG_LAUNCH_CHECK(); return 0; });
+        [&] { (void)lg_launch(residual_norm_kernel<float>, dim3(M), dim3(threads), 0, st, partial, ksplit, M, D, (float*)h, (const float*)norm_w, (float*)xn, eps); LG_LAUNCH_CHECK(); return 0; },
+        [&] { (void)lg_launch(residual_norm_kernel<bf16>, dim3(M), dim3(threads), 0, st, partial, ksplit, M, D, (bf16*)h, (const bf16*)norm_w, (bf16*)xn, eps); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_silu_mul(const float* partial, int ksplit, int M, int F, void* out, int dtype, cudaStream_t st) {
@@ -373,8 +385,8 @@ int launch_silu_mul(const float* partial, int ksplit, int M, int F, void* out, i
     const int blocks = (int)std::min<long long>(((long long)M * F / 4 + 255) / 256, 148 * 16);
     return dispatch_dtype(
         dtype,
-        [&] { silu_mul_kernel<float><<<blocks, 256, 0, st>>>(partial, ksplit, M, F, (float*)out); LG_LAUNCH_CHECK(); return 0; },
-        [&] { silu_mul_kernel<bf16><<<blocks, 256, 0, st>>>(partial, ksplit, M, F, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
+        [&] { (void)lg_launch(silu_mul_kernel<float>, dim3(blocks), dim3(256), 0, st, partial, ksplit, M, F, (float*)out); LG_LAUNCH_CHECK(); return 0; },
+        [&] { (void)lg_launch(silu_mul_kernel<bf16>, dim3(blocks), dim3(256), 0, st, partial, ksplit, M, F, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_store_act(const float* partial, int ksplit, int M, int N, void* out, int gelu, int dtype, cudaStream_t st) {
@@ -382,14 +394,14 @@ int launch_store_act(const float* partial, int ksplit, int M, int N, void* out, 
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
     return dispatch_dtype(
         dtype,
-        [&] { store_act_kernel<float><<<blocks, 256, 0, st>>>(partial, ksplit, total, gelu, (float*)out); LG_LAUNCH_CHECK(); return 0; },
-        [&] { store_act_kernel<bf16><<<blocks, 256, 0, st>>>(partial, ksplit, total, gelu, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
+        [&] { (void)lg_launch(store_act_kernel<float>, dim3(blocks), dim3(256), 0, st, partial, ksplit, total, gelu, (float*)out); LG_LAUNCH_CHECK(); return 0; },
+        [&] { (void)lg_launch(store_act_kernel<bf16>, dim3(blocks), dim3(256), 0, st, partial, ksplit, total, gelu, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_reduce_f32(const float* partial, int ksplit, int M, int N, float* out, cudaStream_t st) {
     const size_t total = (size_t)M * N;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    reduce_f32_kernel<<<blocks, 256, 0, st>>>(partial, ksplit, total, out);
+    (void)lg_launch(reduce_f32_kernel, dim3(blocks), dim3(256), 0, st, partial, ksplit, total, out);
     LG_LAUNCH_CHECK();
     return 0;
 }
@@ -400,7 +412,7 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t st) {
     const int nwarps = ctas >= 592 ? 4 : 8;
     const size_t smem = (size_t)nwarps * (HD + 2) * sizeof(float);
     dim3 grid(a.H, a.R * a.Tq);
-    attention_kernel<T, HD, VEC, LPK><<<grid, nwarps * 32, smem, st>>>(a);
+    (void)lg_launch(attention_kernel<T, HD, VEC, LPK>, dim3(grid), dim3(nwarps * 32), smem, st, a);
     LG_LAUNCH_CHECK();
     return 0;
 }
@@ -421,12 +433,12 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
 }
 
 int launch_advance(int* pos, int* step, cudaStream_t st) {
-    advance_kernel<<<1, 1, 0, st>>>(pos, step);
+    (void)lg_launch(advance_kernel, dim3(1), dim3(1), 0, st, pos, step);
     LG_LAUNCH_CHECK();
     return 0;
 }
 int launch_set_counters(int* pos, int pos_v, int* step, int step_v, cudaStream_t st) {
-    set_counters_kernel<<<1, 1, 0, st>>>(pos, pos_v, step, step_v);
+    (void)lg_launch(set_counters_kernel, dim3(1), dim3(1), 0, st, pos, pos_v, step, step_v);
     LG_LAUNCH_CHECK();
     return 0;
 }

@@ -159,3 +159,28 @@ def test_sampling_run_is_seed_reproducible_and_in_range():
     assert a.dtype == torch.int32 and tuple(a.shape) == (4, 32)
     assert torch.equal(a, b) and not torch.equal(a, c)
     assert int(a.min()) >= 0 and int(a.max()) < 16384
+
+
+def test_attention_kernels_agree_large_batch_t2i(monkeypatch):
+    """The persistent warp-per-item TMA attention (taken when rows*heads >= 592), the CTA-per-item TMA kernel and
+    the CUDA-core kernel must agree on a masked t2i decode at a batch large enough to select each of them."""
+    g = load_golden("gpt_t2i.pt")
+    B, S = 160, 6
+    torch.manual_seed(0)
+    em = torch.zeros(B, 120)
+    lens = torch.randint(3, 120, (B,))
+    for b in range(B):
+        em[b, -int(lens[b]):] = 1
+    cond = (torch.randn(B, 120, 64) * em[:, :, None]).bfloat16()
+    outs = {}
+    for tag, env in (("v2", {"LG_ATTN_TMA": "1", "LG_ATTN_V2": "1"}), ("v1", {"LG_ATTN_TMA": "1", "LG_ATTN_V2": "0"}),
+                     ("cuda_core", {"LG_ATTN_TMA": "0", "LG_ATTN_V2": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = build_gpt(g["cfg"], g["state_dict"], torch.bfloat16)
+        teacher = torch.randint(0, 512, (B, S), generator=torch.Generator().manual_seed(1), dtype=torch.int32)
+        _, logits = _gen(m, cond, S, em, cfg_scale=4.0, teacher=teacher)
+        outs[tag] = logits
+    for tag in ("v2", "v1"):
+        err = (outs[tag] - outs["cuda_core"]).abs().max().item()
+        assert err <= BF16_TOL, (tag, err)
