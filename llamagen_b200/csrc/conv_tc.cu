@@ -1,0 +1,256 @@
+// Blackwell-native implicit-GEMM convolution for the VQ decoder (vq_model.py:128-194):
+//   out[pixel, co] = bias[co] + sum_{tap, ci} in[pixel + tap][ci] * W[co][tap][ci]  (+ residual)
+// on tcgen05 tensor cores with the accumulator in TMEM.
+//
+//  * A operand (UMMA M = 128 pixels): an 8x16-pixel patch x 64 channels of the bf16 NHWC activation, fetched by
+//    ONE 4-D TMA box per (tap, channel chunk). The tap offset is just a signed shift of the box origin and the
+//    3x3 zero padding is TMA's out-of-bounds fill — no im2col buffer, no address arithmetic on the SM.
+//  * B operand (UMMA N = Cout tile <= 128): the weight slab [Cout][tap*Cin + ci] (bf16, K-major), 2-D TMA.
+//  * nearest-2x upsample + 3x3 conv (Upsample, vq_model.py:374-378) is evaluated as four 2x2 "phase" convolutions
+//    on the low-resolution input with pre-summed weights: 16 tap-GEMMs instead of 36 (2.25x fewer FLOPs) and the
+//    upsampled tensor never exists.
+//  * epilogue: all 8 warps drain TMEM (lane = pixel), add bias (+ residual), write bf16 NHWC (or fp32 NCHW for conv_out).
+#include "kernels.cuh"
+#include "tma_utils.cuh"
+#include "umma_utils.cuh"
+#include <algorithm>
+
+namespace {
+
+using namespace tma;
+using namespace umma;
+
+constexpr int kPix = 128;          // pixels per tile (UMMA M)
+constexpr int kCk = 64;            // channels per k-block (128 B)
+constexpr int kConvThreads = 256;
+constexpr int kConvStages = 3;     // 3 x 32 KB -> two CTAs per SM overlap prologue / drain with the other's main loop
+constexpr int kATile = kPix * kCk * 2;
+
+struct ConvTcArgs {
+    int B, Hin, Win, Cin, Hout, Wout, Cout;
+    int mode;            // 0: 3x3 pad 1   1: 1x1   2: nearest-2x + 3x3 as 2x2 phase convs
+    int bh, bw;          // pixel patch, bh*bw == 128
+    int tiles_x, tiles_y;
+    int bn;              // Cout tile (multiple of 16, <= 128)
+    int kchunks;         // Cin / 64
+    int ntaps;           // 9, 1 or 4
+    int tmem_cols;
+    const float* bias;
+    const bf16* residual;
+    bf16* out_bf;
+    float* out_nchw;
+};
+
+__global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap amap,
+                                                                  const __grid_constant__ CUtensorMap wmap, ConvTcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int b_tile_bytes = a.bn * kCk * 2;
+    const int stage_bytes = kATile + ((b_tile_bytes + 1023) / 1024) * 1024;
+    uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kConvStages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kConvStages;
+    uint64_t* tmem_full_bar = empty_bar + kConvStages;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int b = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - b * tiles_per_img;
+    const int y0 = (trem / a.tiles_x) * a.bh, x0 = (trem % a.tiles_x) * a.bw;
+    const int n0 = blockIdx.y * a.bn;
+    const int phase = blockIdx.z, py = phase >> 1, px = phase & 1;
+    const int nkb = a.ntaps * a.kchunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_map(&amap);
+        prefetch_map(&wmap);
+        for (int s = 0; s < kConvStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_slot, (uint32_t)a.tmem_cols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t tx = (uint32_t)(kATile + b_tile_bytes);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kConvStages;
+                const uint32_t ph = (uint32_t)((i / kConvStages) & 1);
+                const int tap = i / a.kchunks, cc = i - tap * a.kchunks;
+                int dy = 0, dx = 0;
+                if (a.mode == 0) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                else if (a.mode == 2) { const int ta = tap >> 1, tb = tap & 1; dy = py == 0 ? ta - 1 : ta; dx = px == 0 ? tb - 1 : tb; }
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], tx);
+                uint8_t* sa = tiles + s * stage_bytes;
+                load_4d(sa, &amap, &full_bar[s], cc * kCk, x0 + dx, y0 + dy, b);
+                load_2d(sa + kATile, &wmap, &full_bar[s], tap * a.Cin + cc * kCk, phase * a.Cout + n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc(a.bn);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % kConvStages;
+            const uint32_t ph = (uint32_t)((i / kConvStages) & 1);
+            mbar_wait(&full_bar[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(tiles + s * stage_bytes);
+                const uint64_t adesc = make_desc_sw128(sa);
+                const uint64_t bdesc = make_desc_sw128(sa + kATile);
+#pragma unroll
+                for (int k = 0; k < kCk / 16; ++k)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
+                umma_commit(&empty_bar[s]);
+                if (i == nkb - 1) umma_commit(tmem_full_bar);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---------------------------------------------------------------------- drain: lane = pixel of the patch
+    {
+        const int q = warp & 3, half = warp >> 2;
+        const int pix = q * 32 + lane;
+        const int iy = pix / a.bw, ix = pix - iy * a.bw;
+        int oy = y0 + iy, ox = x0 + ix;
+        const bool inb = oy < a.Hin && ox < a.Win;     // patches may overhang the image (TMA zero-filled the reads)
+        if (a.mode == 2) { oy = 2 * oy + py; ox = 2 * ox + px; }
+        const int cols_half = ((a.bn / 16 + 1) / 2) * 16;
+        const int c_begin = half * cols_half, c_end = min(a.bn, c_begin + cols_half);
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const size_t opix = ((size_t)b * a.Hout + oy) * a.Wout + ox;
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            const int n = n0 + c0;
+            if (!inb || n >= a.Cout) continue;
+            float f[16];
+            if (n + 16 <= a.Cout) {
+                const float4* bp = reinterpret_cast<const float4*>(a.bias + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 bv = __ldg(bp + j);
+                    f[4 * j] = __uint_as_float(v[4 * j]) + bv.x;
+                    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv.y;
+                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv.z;
+                    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (n + j < a.Cout ? a.bias[n + j] : 0.f);
+            }
+            if (a.out_nchw) {       // conv_out: fp32 NCHW, Cout = 3
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n + j < a.Cout) a.out_nchw[(((size_t)b * a.Cout + n + j) * a.Hout + oy) * a.Wout + ox] = f[j];
+                continue;
+            }
+            bf16* op = a.out_bf + opix * a.Cout + n;
+            if (a.residual) {
+                const uint4* rp = reinterpret_cast<const uint4*>(a.residual + opix * a.Cout + n);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint4 r = rp[hh];
+                    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        f[8 * hh + 2 * j] += __uint_as_float(w[j] << 16);
+                        f[8 * hh + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+                    }
+                }
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+// W'[phase][co][a*2+b][ci] = sum of the 3x3 taps that land on input offset (a, b) for output parity (py, px)
+__global__ void upsample_phase_weights_kernel(const float* __restrict__ w /*[Cout][Cin][3][3]*/, bf16* __restrict__ out,
+                                              int cout, int cin) {
+    const size_t total = (size_t)4 * cout * 4 * cin;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin);
+        const int t = (int)((i / cin) % 4);
+        const int co = (int)((i / ((size_t)cin * 4)) % cout);
+        const int p = (int)(i / ((size_t)cin * 4 * cout));
+        const int py = p >> 1, px = p & 1, ta = t >> 1, tb = t & 1;
+        // rows: py==0: a=0 -> ky {0}, a=1 -> ky {1,2};  py==1: a=0 -> ky {0,1}, a=1 -> ky {2}   (same for columns)
+        const int ky0 = py == 0 ? (ta == 0 ? 0 : 1) : (ta == 0 ? 0 : 2), ky1 = py == 0 ? (ta == 0 ? 0 : 2) : (ta == 0 ? 1 : 2);
+        const int kx0 = px == 0 ? (tb == 0 ? 0 : 1) : (tb == 0 ? 0 : 2), kx1 = px == 0 ? (tb == 0 ? 0 : 2) : (tb == 0 ? 1 : 2);
+        float s = 0.f;
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) s += w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx];
+        out[i] = __float2bfloat16_rn(s);
+    }
+}
+
+}  // namespace
+
+int conv_tc_make_phase_weights(const float* w_f32, bf16* out, int cout, int cin, cudaStream_t st) {
+    upsample_phase_weights_kernel<<<148 * 4, 256, 0, st>>>(w_f32, out, cout, cin);
+    LG_LAUNCH_CHECK();
+    return 0;
+}
+
+bool conv_tc_supported(int Hin, int Win, int Cin, int Cout, int ksize, int up, bool nchw_out) {
+    if (Cin % 64 != 0) return false;
+    if (Win < 8 || Hin < 8) return false;
+    if (!nchw_out && Cout % 16 != 0) return false;
+    if (up && ksize != 3) return false;
+    return ksize == 1 || ksize == 3;
+}
+
+// weights: up == 0 -> [Cout][k*k][Cin] bf16 ; up == 1 -> phase weights [4][Cout][4][Cin] bf16
+int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16* weights, const float* bias, int Cout,
+                   int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st) {
+    ConvTcArgs a;
+    a.B = B; a.Hin = Hin; a.Win = Win; a.Cin = Cin; a.Cout = Cout;
+    a.Hout = up ? 2 * Hin : Hin; a.Wout = up ? 2 * Win : Win;
+    a.mode = up ? 2 : (ksize == 1 ? 1 : 0);
+    a.ntaps = up ? 4 : ksize * ksize;
+    a.bw = Win >= 16 ? 16 : 8;
+    a.bh = kPix / a.bw;
+    a.tiles_x = cdiv(Win, a.bw);
+    a.tiles_y = cdiv(Hin, a.bh);
+    a.bn = std::min(128, ((Cout + 15) / 16) * 16);
+    a.kchunks = Cin / kCk;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < a.bn) a.tmem_cols *= 2;
+    a.bias = bias; a.residual = residual; a.out_bf = out_bf; a.out_nchw = out_nchw;
+
+    CUtensorMap amap, wmap;
+    LG_TRY(tma::make_map_nhwc(&amap, in, (uint64_t)B, (uint64_t)Hin, (uint64_t)Win, (uint64_t)Cin, (uint32_t)a.bh, (uint32_t)a.bw, kCk));
+    const uint64_t wrows = (uint64_t)(up ? 4 : 1) * Cout, wcols = (uint64_t)a.ntaps * Cin;
+    LG_TRY(tma::make_map_2d(&wmap, weights, wrows, wcols, wcols, (uint32_t)a.bn, kCk));
+
+    const int b_tile_bytes = a.bn * kCk * 2;
+    const int stage_bytes = kATile + ((b_tile_bytes + 1023) / 1024) * 1024;
+    const size_t smem = 1024 + (size_t)kConvStages * stage_bytes + (2 * kConvStages + 1) * sizeof(uint64_t) + 16;
+    static bool attr = false;
+    if (!attr) {
+        LG_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        attr = true;
+    }
+    LG_REQUIRE(smem <= 110 * 1024, "conv_tc: shared memory %zu too large", smem);
+    dim3 grid((unsigned)(B * a.tiles_x * a.tiles_y), (unsigned)cdiv(Cout, a.bn), up ? 4 : 1);
+    conv_tc_kernel<<<grid, kConvThreads, smem, st>>>(amap, wmap, a);
+    LG_LAUNCH_CHECK();
+    return 0;
+}

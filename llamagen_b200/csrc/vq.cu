@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(128) argmin_kernel(const float* __restrict__ z
 
 // ------------------------------------------------------------------------------------------------ model structs
 struct HostTensor { const float* p = nullptr; int64_t shape[4] = {0, 0, 0, 0}; int ndim = 0; };
-struct ConvW { bf16* w = nullptr; const float* bias = nullptr; int cout = 0, cin = 0, k = 0; };
+struct ConvW { bf16* w = nullptr; bf16* w_phase = nullptr; const float* bias = nullptr; int cout = 0, cin = 0, k = 0; };
 struct NormW { const float* gamma = nullptr; const float* beta = nullptr; int c = 0; };
 struct ResW { NormW n1, n2; ConvW c1, c2, nin; bool has_nin = false; int cin = 0, cout = 0; };
 struct AttnW { NormW norm; ConvW qk, v, proj; float* qk_bias = nullptr; int c = 0; };
@@ -423,6 +423,12 @@ int chunk_images(const lg_vq* v, int B, int g) {
 // ---- layer launchers --------------------------------------------------------------------------------
 int run_conv(const ConvW& cw, const bf16* in, int B, int Hin, int Win, int up, const bf16* residual, bf16* out_bf,
              float* out_nchw, cudaStream_t st) {
+    if (lg_env_flag("LG_CONV_TC", 1) && conv_tc_supported(Hin, Win, cw.cin, cw.cout, cw.k, up, out_nchw != nullptr) &&
+        (!up || cw.w_phase)) {
+        LG_PROF(PC_VQ_CONV, st, launch_conv_tc(in, B, Hin, Win, cw.cin, up ? cw.w_phase : cw.w, cw.bias, cw.cout, cw.k, up, residual,
+                                               out_bf, out_nchw, st));
+        return 0;
+    }
     const int Hout = up ? 2 * Hin : Hin, Wout = up ? 2 * Win : Win;
     const int M = B * Hout * Wout, K = cw.k * cw.k * cw.cin;
     mma::ConvA al{in, Hin, Win, cw.cin, Hout, Wout, cw.k, up, M};
@@ -577,7 +583,16 @@ int lg_vq_finalize(lg_vq* v, void* stream) {
             }
         }
         lv.up = i_level != 0;
-        if (lv.up) LG_TRY(make_conv(v, "decoder.conv_blocks." + std::to_string(bi) + ".upsample.conv", block_in, block_in, 3, &lv.upconv, st));
+        if (lv.up) {
+            const std::string un = "decoder.conv_blocks." + std::to_string(bi) + ".upsample.conv";
+            LG_TRY(make_conv(v, un, block_in, block_in, 3, &lv.upconv, st));
+            if (block_in % 64 == 0) {   // pre-summed 2x2 phase weights for the tcgen05 upsample path (conv_tc.cu)
+                const float* wf = nullptr;
+                LG_TRY(get(v, un + ".weight", {block_in, block_in, 3, 3}, &wf));
+                LG_TRY(dev_alloc(v, (size_t)16 * block_in * block_in, &lv.upconv.w_phase));
+                LG_TRY(conv_tc_make_phase_weights(wf, lv.upconv.w_phase, block_in, block_in, st));
+            }
+        }
         v->levels.push_back(lv);
     }
     LG_TRY(make_norm(v, "decoder.norm_out", block_in, &v->norm_out));

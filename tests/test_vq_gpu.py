@@ -46,8 +46,12 @@ def test_tiny_argmin_matches_reference_golden():
     assert torch.equal(idx, g["argmin"])
 
 
+@pytest.mark.parametrize("conv", ["tcgen05", "mma"])
 @pytest.mark.parametrize("name,g,B", [("VQ-16", 16, 3), ("VQ-16", 24, 1), ("VQ-8", 16, 2)])
-def test_full_decoder_vs_oracle(name, g, B):
+def test_full_decoder_vs_oracle(name, g, B, conv, monkeypatch):
+    """conv=tcgen05: TMA 4-D box + UMMA/TMEM implicit GEMM (conv_tc.cu, incl. the 2x2 phase form of upsample+conv and
+    24x24 grids whose 8x16 patches overhang the image); conv=mma: the mma.sync + cp.async gather path."""
+    monkeypatch.setenv("LG_CONV_TC", "1" if conv == "tcgen05" else "0")
     from llamagen_b200 import VQ_models
     torch.manual_seed(g + B)
     m = VQ_models[name](codebook_size=16384, codebook_embed_dim=8).cuda().eval()
