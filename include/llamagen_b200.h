@@ -139,6 +139,10 @@ int  lg_vq_argmin(lg_vq* v, const float* z_nchw, int B, int grid, int64_t* out_i
  * While enabled, launches are bracketed by CUDA events on the launching stream (CUDA-graph replay is bypassed).
  * lg_profile_read synchronises the device and returns the summed duration / launch count of one class
  * (class ids: see `lg_profile_class_name`). */
+/* Toggle programmatic dependent launch for subsequent launches (default: on, or LG_PDL=0/1). With it off, CUPTI
+ * kernel durations are additive (no early-started kernels waiting on their dependency), which is what the
+ * roofline leg of bench.py traces. */
+int         lg_set_pdl(int on);
 int         lg_profile_enable(int on);
 int         lg_profile_reset(void);
 int         lg_profile_read(int cls, double* total_ms, uint64_t* launches);

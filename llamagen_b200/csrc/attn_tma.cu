@@ -15,7 +15,7 @@ namespace {
 using namespace tma;
 
 constexpr int kKC = 64;        // keys per stage
-constexpr int kStagesA = 3;
+constexpr int kStagesA = 2;    // 2 x 16 KB per CTA -> 6 CTAs (24 warps) per SM; contexts here are <= 1144 keys
 constexpr int kWarps = 4;      // each warp owns 16 keys of a stage
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -48,7 +48,7 @@ struct AttnTmaArgs {
 };
 
 template <int HD>
-__global__ void __launch_bounds__(kWarps * 32) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
+__global__ void __launch_bounds__(kWarps * 32, HD == 64 ? 6 : 3) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
                                                                const __grid_constant__ CUtensorMap vmap, AttnTmaArgs a) {
     constexpr int NSUB = HD / 64;                 // 128-byte-wide sub-tiles per row
     constexpr int SUB_BYTES = kKC * 128;          // one [64 keys][64 dims] bf16 sub-tile
@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(kWarps * 32) attn_tma_kernel(const __grid_cons
         fence_barrier_init();
     }
     __syncthreads();
-    lg_pdl_sync();     // the K/V rows of this step (and the position counter) were written by earlier kernels
+    // Programmatic dependent launch: only the LAST chunk (the one holding this step's key, written by the
+    // immediately preceding RoPE/KV-write kernel) and q depend on the predecessor. Every older key row and the
+    // position counter were produced at least one kernel earlier, so their TMA loads are issued before the
+    // dependency wait and overlap the predecessor's execution.
     const int qpos = (a.pos_dev ? *a.pos_dev : 0) + a.pos_value;
     const int nkeys = qpos + 1;
     const int nchunks = (nkeys + kKC - 1) / kKC;
@@ -86,8 +89,12 @@ __global__ void __launch_bounds__(kWarps * 32) attn_tma_kernel(const __grid_cons
             load_2d(vt + sub * SUB_BYTES, &vmap, &full_bar[s], sub * 64, (int)(row0 + (long long)ci * kKC));
         }
     };
+    const int npro = min(kStagesA, nchunks);
     if (threadIdx.x == 0)
-        for (int ci = 0; ci < min(kStagesA, nchunks); ++ci) issue(ci);
+        for (int ci = 0; ci < npro; ++ci)
+            if (ci != nchunks - 1) issue(ci);
+    lg_pdl_sync();
+    if (threadIdx.x == 0 && nchunks - 1 < npro) issue(nchunks - 1);
 
     // q as the A operand of m16n8k16: only MMA row 0 (lanes with g == 0) is real, the other 15 rows are zero
     uint32_t qa[HD / 16][2];
@@ -414,9 +421,10 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     t.emb_mask = a.emb_mask; t.B = a.B; t.Tc = a.Tc; t.scale = a.scale;
     const CUtensorMap& km = *reinterpret_cast<const CUtensorMap*>(a.kmap);
     const CUtensorMap& vm = *reinterpret_cast<const CUtensorMap*>(a.vmap);
-    // v2 (persistent warp-per-item) when there are enough items to fill the machine; the CTA-per-item kernel
-    // keeps the batch-1 latency path (few items, 4 warps split the keys of one item).
-    const bool v2 = lg_env_flag("LG_ATTN_V2", 1) && a.R * a.H >= 4 * 148 && a.hd == 64;
+    // v2 (persistent warp-per-item, LG_ATTN_V2=1) measured SLOWER than the CTA-per-item kernel on B200 (25.7 vs
+    // 19.1 us at R=128, c=128: with one warp per scheduler the ldmatrix->mma->softmax chain is latency-bound), so it
+    // stays opt-in; profiles/ keeps both ncu captures.
+    const bool v2 = lg_env_flag("LG_ATTN_V2", 0) && a.R * a.H >= 4 * 148 && a.hd == 64;
     if (v2) return launch_v2<64>(km, vm, t, st);
     if (a.hd == 64) return launch_t<64>(km, vm, t, st);
     return launch_t<128>(km, vm, t, st);

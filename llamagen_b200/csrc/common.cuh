@@ -67,10 +67,10 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // is visible. Inside the captured CUDA graph these become programmatic dependency edges.
 // ---------------------------------------------------------------------------------------------
 int lg_env_flag(const char* name, int dflt);
+extern int g_lg_pdl;     // -1: read LG_PDL from the environment on first use
 inline bool lg_pdl_enabled() {
-    static int v = -1;
-    if (v < 0) v = lg_env_flag("LG_PDL", 1) ? 1 : 0;
-    return v == 1;
+    if (g_lg_pdl < 0) g_lg_pdl = lg_env_flag("LG_PDL", 1) ? 1 : 0;
+    return g_lg_pdl == 1;
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t lg_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

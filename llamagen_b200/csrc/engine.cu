@@ -28,6 +28,7 @@ int lg_fail(const char* fmt, ...) {
     return -1;
 }
 std::atomic<uint64_t> g_lg_launches{0};
+int g_lg_pdl = -1;
 int lg_env_flag(const char* name, int dflt) {
     const char* e = getenv(name);
     if (!e || !e[0]) return dflt;
@@ -147,7 +148,7 @@ struct lg_engine {
                 cudaStream_t st);
     int embed_cond(const void* cond, int B, int R, int T, cudaStream_t st);
     int gemm(const void* x, int M, int N, int K, const void* wa, const void* wb, int n_split, int* ksplit,
-             float* direct_out, cudaStream_t st);
+             float* direct_out, cudaStream_t st, const GemmNext* next = nullptr);
 };
 
 size_t lg_engine::carve(Workspace& o, char* base, int rows, int max_seq) const {
@@ -190,12 +191,12 @@ size_t lg_engine::carve(Workspace& o, char* base, int rows, int max_seq) const {
 }
 
 int lg_engine::gemm(const void* x, int M, int N, int K, const void* wa, const void* wb, int n_split, int* ksplit,
-                    float* direct_out, cudaStream_t st) {
+                    float* direct_out, cudaStream_t st, const GemmNext* next) {
     // when the plan needs a single slab the GEMM can write straight into `direct_out`
     const size_t slabs = gemm_partial_floats(M, N, K, cfg.dtype) / ((size_t)M * N);
     float* dst = (direct_out && slabs == 1) ? direct_out : ws.partial;
     GemmPlan plan;
-    LG_TRY(gemm_partial(x, K, wa, wb, n_split, M, N, K, cfg.dtype, dst, &plan, st));
+    LG_TRY(gemm_partial(x, K, wa, wb, n_split, M, N, K, cfg.dtype, dst, &plan, st, next));
     *ksplit = plan.ksplit;
     return dst == direct_out ? 1 : 0;
 }
@@ -211,7 +212,12 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         const Layer& ly = layers[l];
         char* kc = ws.kcache + (size_t)l * ws.layer_cache_bytes;
         char* vc = ws.vcache + (size_t)l * ws.layer_cache_bytes;
-        LG_PROF(PC_GEMM_QKV, st, gemm(ws.xn, M, 3 * D, D, ly.wqkv, nullptr, 0, &ks, nullptr, st));
+        const size_t eb = esz;
+        GemmNext nx_wo{ly.wo, (size_t)D * D * eb, nullptr, 0};
+        GemmNext nx_w13{ly.w1, (size_t)F * D * eb, ly.w3, (size_t)F * D * eb};
+        GemmNext nx_w2{ly.w2, (size_t)D * F * eb, nullptr, 0};
+        GemmNext nx_qkv{(l + 1 < L) ? layers[l + 1].wqkv : output, (l + 1 < L) ? (size_t)3 * D * D * eb : (size_t)V * D * eb, nullptr, 0};
+        LG_PROF(PC_GEMM_QKV, st, gemm(ws.xn, M, 3 * D, D, ly.wqkv, nullptr, 0, &ks, nullptr, st, &nx_wo));
         QkvEpiArgs qa;
         qa.partial = ws.partial; qa.ksplit = ks; qa.M = M; qa.Tq = Tq; qa.D = D; qa.H = H; qa.hd = hd;
         qa.pos = pos; qa.freqs = freqs; qa.q = ws.q; qa.kcache = kc; qa.vcache = vc; qa.maxS = ws.max_seq; qa.dtype = dt;
@@ -225,11 +231,11 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
             aa.cache_row_base = (long long)l * ws.rows * H * ws.max_seq;
         }
         LG_PROF(PC_ATTENTION, st, launch_attention(aa, st));
-        LG_PROF(PC_GEMM_WO, st, gemm(ws.attn, M, D, D, ly.wo, nullptr, 0, &ks, nullptr, st));
+        LG_PROF(PC_GEMM_WO, st, gemm(ws.attn, M, D, D, ly.wo, nullptr, 0, &ks, nullptr, st, &nx_w13));
         LG_PROF(PC_RESNORM, st, launch_residual_norm(ws.partial, ks, M, D, ws.h, ly.ffn_norm, ws.xn, cfg.norm_eps, dt, st));
-        LG_PROF(PC_GEMM_W13, st, gemm(ws.xn, M, 2 * F, D, ly.w1, ly.w3, F, &ks, nullptr, st));
+        LG_PROF(PC_GEMM_W13, st, gemm(ws.xn, M, 2 * F, D, ly.w1, ly.w3, F, &ks, nullptr, st, &nx_w2));
         LG_PROF(PC_SILU, st, launch_silu_mul(ws.partial, ks, M, F, ws.ff, dt, st));
-        LG_PROF(PC_GEMM_W2, st, gemm(ws.ff, M, D, F, ly.w2, nullptr, 0, &ks, nullptr, st));
+        LG_PROF(PC_GEMM_W2, st, gemm(ws.ff, M, D, F, ly.w2, nullptr, 0, &ks, nullptr, st, &nx_qkv));
         const void* next_norm = (l + 1 < L) ? layers[l + 1].attn_norm : final_norm;
         LG_PROF(PC_RESNORM, st, launch_residual_norm(ws.partial, ks, M, D, ws.h, next_norm, ws.xn, cfg.norm_eps, dt, st));
     }
@@ -241,7 +247,8 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
     }
     (void)round_out;
     prof_begin(PC_GEMM_HEAD, st);
-    const int direct = gemm(xlast, R, V, D, output, nullptr, 0, &ks, logits_out, st);
+    GemmNext nx_first{layers[0].wqkv, (size_t)3 * D * D * esz, nullptr, 0};   // the next decode step starts with layer 0
+    const int direct = gemm(xlast, R, V, D, output, nullptr, 0, &ks, logits_out, st, &nx_first);
     prof_end(st);
     if (direct < 0) return direct;
     if (direct == 0) LG_TRY(launch_reduce_f32(ws.partial, ks, R, V, logits_out, st));
@@ -540,6 +547,10 @@ static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, 
     return ret;
 }
 
+int lg_set_pdl(int on) {
+    g_lg_pdl = on ? 1 : 0;
+    return 0;
+}
 int lg_profile_enable(int on) {
     if (!on) prof_drain();
     g_prof.on = on != 0;

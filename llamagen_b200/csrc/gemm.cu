@@ -97,7 +97,7 @@ Plan make_plan(int M, int N, int K, int dtype) {
     Plan p;
     p.tc = false;
     p.skinny = (dtype == LG_DTYPE_F32) || M <= kSkinnyRT;
-    if (!p.skinny && lg_env_flag("LG_GEMM_TC", 0) && gemm_tc_supported(M, N, K, dtype) && N % 128 == 0) {
+    if (!p.skinny && lg_env_flag("LG_GEMM_TC", 1) && gemm_tc_supported(M, N, K, dtype) && N % 128 == 0) {
         p.tc = true;
         p.bm = 0;
         p.ksplit = gemm_tc_ksplit(M, N, K);
@@ -127,7 +127,7 @@ size_t gemm_partial_floats(int M, int N, int K, int dtype) {
 }
 
 int gemm_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K, int dtype,
-                 float* partial, GemmPlan* plan, cudaStream_t st) {
+                 float* partial, GemmPlan* plan, cudaStream_t st, const GemmNext* next) {
     LG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %d %d %d", M, N, K);
     LG_REQUIRE(N % 2 == 0 && K % 8 == 0, "gemm: N=%d must be even and K=%d a multiple of 8", N, K);
     if (Wb == nullptr) { Wb = Wa; n_split = N; }
@@ -157,7 +157,7 @@ int gemm_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_s
     }
     if (p.tc) {
         if (n_split % 128 != 0 && n_split != N) return lg_fail("gemm: weight segment boundary %d not tile aligned", n_split);
-        return gemm_tc_partial(X, ldx, Wa, Wb, n_split, M, N, K, partial, nullptr, st);
+        return gemm_tc_partial(X, ldx, Wa, Wb, n_split, M, N, K, partial, nullptr, st, next);
     }
     mma::DenseA al{(const bf16*)X, ldx, 0, M};
     mma::BRows bw{(const bf16*)Wa, (const bf16*)Wb, n_split, K, 0, N};

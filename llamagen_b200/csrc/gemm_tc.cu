@@ -40,6 +40,8 @@ struct TcArgs {
     int tmem_cols;        // power of two >= max(32, rpad)
     int stages;           // smem ring depth (<= kMaxStages), sized to fit 227 KB
     float* partial;       // [ksplit][M][N]
+    const char* pf0; unsigned long long pfb0;   // next GEMM's weights to pull into L2 (see GemmNext)
+    const char* pf1; unsigned long long pfb1;
     unsigned long long* trace;   // debug: [cta][8] %globaltimer stamps of the pipeline phases (nullable)
 };
 
@@ -117,6 +119,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 uint8_t* sa = tiles + s * stage_bytes;
                 load_2d(sa, wmap, &full_bar[s], (kb0 + i) * kBlockK, wrow);
                 load_2d(sa + kATileBytes, &map_x, &full_bar[s], (kb0 + i) * kBlockK, 0);
+            }
+            // ask L2 for this CTA's share of the next GEMM's weights (static chain: qkv -> wo -> w1|w3 -> w2 -> next qkv)
+            {
+                const unsigned long long cta = (unsigned long long)blockIdx.y * gridDim.x + blockIdx.x;
+                const unsigned long long ncta = (unsigned long long)gridDim.x * gridDim.y;
+                const char* pp[2] = {a.pf0, a.pf1};
+                const unsigned long long bb[2] = {a.pfb0, a.pfb1};
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (!bb[t]) continue;
+                    const unsigned long long per = ((bb[t] + ncta - 1) / ncta + 4095ull) & ~4095ull;
+                    unsigned long long off = cta * per;
+                    const unsigned long long end = off + per < bb[t] ? off + per : bb[t];
+                    for (; off < end; off += 16384ull) {
+                        const unsigned long long len = end - off < 16384ull ? end - off : 16384ull;
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp[t] + off), "r"((uint32_t)(len & ~15ull)) : "memory");
+                    }
+                }
             }
             TC_TRACE(2);
         }
@@ -246,7 +266,7 @@ extern "C" void lg_debug_set_tc_trace(unsigned long long* dev_buf) { g_tc_trace 
 int gemm_tc_ksplit(int M, int N, int K) {
     (void)M;
     const int tiles = cdiv(N, kBlockN), kb = cdiv(K, kBlockK);
-    int ks = std::max(1, 148 / std::max(tiles, 1));
+    int ks = std::max(1, lg_env_flag("LG_TC_CTAS", 148) / std::max(tiles, 1));
     ks = std::min(ks, std::max(1, kb / 2));
     return std::min(ks, 16);
 }
@@ -256,7 +276,7 @@ bool gemm_tc_supported(int M, int N, int K, int dtype) {
 }
 
 int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
-                    float* partial, int* ksplit_out, cudaStream_t st) {
+                    float* partial, int* ksplit_out, cudaStream_t st, const GemmNext* next) {
     LG_REQUIRE(gemm_tc_supported(M, N, K, LG_DTYPE_BF16), "gemm_tc: unsupported shape %d %d %d", M, N, K);
     if (Wb == nullptr) { Wb = Wa; n_split = N; }
     LG_REQUIRE(n_split % kBlockN == 0 || n_split == N, "gemm_tc: weight segment boundary %d must be a multiple of %d", n_split, kBlockN);
@@ -283,6 +303,9 @@ int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int 
     a.stages = std::min(std::min(kMaxStages, lg_env_flag("LG_TC_STAGES", kMaxStages)), (int)((225 * 1024 - 1024) / stage_bytes));
     a.stages = std::min(a.stages, std::max(2, a.kblocks_per_split));   // never more stages than k-blocks
     a.trace = g_tc_trace;
+    const bool pf = next && lg_env_flag("LG_L2_PREFETCH", 1);
+    a.pf0 = pf ? (const char*)next->p0 : nullptr; a.pfb0 = pf ? next->b0 : 0;
+    a.pf1 = pf ? (const char*)next->p1 : nullptr; a.pfb1 = pf ? next->b1 : 0;
     LG_REQUIRE(a.stages >= 2, "gemm_tc: tile too large for a 2-stage ring");
     const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
     static bool attr = false;

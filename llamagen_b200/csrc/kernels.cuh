@@ -36,10 +36,16 @@ int launch_sample(const SampleArgs& a, cudaStream_t st);
 struct GemmPlan {
     int ksplit;            // number of fp32 partial slabs written
 };
+// Weights the NEXT GEMM of the decode chain will stream: the current GEMM's CTAs ask the L2 to fetch them
+// (cp.async.bulk.prefetch.L2) so the next kernel's TMA loads hit L2 instead of paying the HBM latency.
+struct GemmNext {
+    const void* p0 = nullptr; size_t b0 = 0;
+    const void* p1 = nullptr; size_t b1 = 0;
+};
 // Returns the plan used; partial must hold ksplit_max(M,N,K) * M * N floats (see gemm_partial_floats).
 size_t gemm_partial_floats(int M, int N, int K, int dtype);
 int gemm_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
-                 int dtype, float* partial, GemmPlan* plan, cudaStream_t st);
+                 int dtype, float* partial, GemmPlan* plan, cudaStream_t st, const GemmNext* next = nullptr);
 
 // ------------------------------------------------------------------------------------------------
 // xf_kernels.cu — transformer glue kernels (all templated on the activation dtype internally)
@@ -110,7 +116,7 @@ int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16*
 int gemm_tc_ksplit(int M, int N, int K);
 bool gemm_tc_supported(int M, int N, int K, int dtype);
 int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
-                    float* partial, int* ksplit_out, cudaStream_t st);
+                    float* partial, int* ksplit_out, cudaStream_t st, const GemmNext* next = nullptr);
 
 // *pos += 1; *step += 1  (device-side loop counters for graph replay)
 int launch_advance(int* pos, int* step, cudaStream_t st);
