@@ -45,6 +45,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-roofline", action="store_true")
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--latency", action="store_true",
+                   help="extra leg: per-token decode latency at batch 1 (R=2 rows under CFG), AR sampling only")
     return p.parse_args()
 
 
@@ -446,6 +448,25 @@ def run_ours(args):
                                  "vq_floor_ms": round(vq_roof_ms, 2), "measured_ms_per_step": round(ms / args.steps, 2),
                                  "frac_of_floor": round((step_roof_ms * S + vq_roof_ms) / (ms / args.steps), 4),
                                  "traced_ar_kernel_ms": round(total_ms - total_vq, 2), "traced_vq_kernel_ms": round(total_vq, 2)}
+
+    # ---------------- batch-1 per-token latency (BASELINE.json metric, second half), rank 0, on request
+    if rank == 0 and args.latency:
+        lab1 = torch.randint(0, 1000, (1,), device=dev)
+        for _ in range(3):
+            generate(gpt, lab1, S, **kw)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        reps = 5
+        for _ in range(reps):
+            generate(gpt, lab1, S, **kw)
+        ev1.record()
+        torch.cuda.synchronize()
+        us_tok = 1000.0 * ev0.elapsed_time(ev1) / reps / S
+        alg1 = algorithmic(args.gpt_model, 2, S)
+        floor_us = 1e6 * alg1["step_bytes"] / (peaks()["hbm_gbs"] * 1e9)
+        line["latency_b1"] = {"us_per_token": round(us_tok, 2), "hbm_floor_us": round(floor_us, 2), "frac_of_hbm_roofline": round(floor_us / us_tok, 4),
+                              "rows": 2, "note": "generate() of 1 image incl. prefill and sampling, / tokens"}
 
     # ---------------- CPU baseline leg (rank 0, N=1 only): bounded sample of the same workload on the host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

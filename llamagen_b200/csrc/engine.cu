@@ -111,6 +111,7 @@ struct Workspace {
     int32_t* tokens = nullptr;
     int* counters = nullptr;  // [0] = pos, [1] = step
     size_t layer_cache_bytes = 0;
+    size_t partial_floats = 0;
     alignas(64) unsigned char kmap[128];   // CUtensorMap over the K / V cache regions (bf16 only)
     alignas(64) unsigned char vmap[128];
     bool have_maps = false;
@@ -133,14 +134,18 @@ struct lg_engine {
     const void *final_norm = nullptr, *output = nullptr;
     const float* freqs = nullptr;
     bool finalized = false;
-    Workspace ws;
+    Workspace ws;                         // ACTIVE workspace (full, or one of the two halves while a group is issued)
+    Workspace full, sub[2];               // sub[g]: rows/2 each, carved INSIDE the regions of `full` (dual-chain decode)
+    bool can_split = false;
     bool use_graph = true;
-    cudaStream_t work = nullptr;          // engine-owned stream the generate loop (and its graph) runs on
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t work = nullptr, work2 = nullptr;   // engine-owned streams the generate loop (and its graphs) run on
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     ~lg_engine() {
         if (work) cudaStreamDestroy(work);
+        if (work2) cudaStreamDestroy(work2);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_join2) cudaEventDestroy(ev_join2);
     }
 
     size_t carve(Workspace& o, char* base, int rows, int max_seq) const;
@@ -181,6 +186,7 @@ size_t lg_engine::carve(Workspace& o, char* base, int rows, int max_seq) const {
         if (cfg.model_type == LG_MODEL_T2I) pf = std::max(pf, gemm_partial_floats(M, D, cfg.caption_dim, cfg.dtype));
     }
     pf = std::max(pf, gemm_partial_floats(rows, V, D, cfg.dtype));
+    o.partial_floats = pf;
     o.partial = (float*)take(pf * sizeof(float));
     o.logits = (float*)take((size_t)rows * V * sizeof(float));
     o.tokens = (int32_t*)take((size_t)rows * sizeof(int32_t));
@@ -396,13 +402,52 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
             tmp.have_maps = true;
         }
     }
+    e->full = tmp;
     e->ws = tmp;
+    // Two half-batch workspaces inside the same memory (every region scales with rows, so each half takes one half
+    // of every region; the K/V halves stay inside the zero-initialised cache regions).
+    e->can_split = false;
+    if (rows % 2 == 0 && rows / 2 >= 32 && e->cfg.dtype == LG_DTYPE_BF16 && tmp.have_maps) {
+        const lg_model_cfg& c = e->cfg;
+        const int hr = rows / 2;
+        const int Tc = c.model_type == LG_MODEL_T2I ? c.cls_token_num : 1;
+        const size_t Mh = (size_t)hr * Tc, esz = e->esz;
+        Workspace probe;
+        e->carve(probe, nullptr, hr, max_seq);
+        const size_t pf_full = tmp.partial_floats, pf_half = probe.partial_floats;
+        if (pf_half <= pf_full / 2 / 64 * 64) {
+            for (int g = 0; g < 2; ++g) {
+                Workspace w = tmp;
+                w.rows = hr;
+                w.layer_cache_bytes = (size_t)hr * c.n_head * max_seq * e->hd * esz;
+                w.kcache = tmp.kcache + (size_t)g * w.layer_cache_bytes * c.n_layer;
+                w.vcache = tmp.vcache + (size_t)g * w.layer_cache_bytes * c.n_layer;
+                w.h = tmp.h + (size_t)g * Mh * c.dim * esz;
+                w.xn = tmp.xn + (size_t)g * Mh * c.dim * esz;
+                w.q = tmp.q + (size_t)g * Mh * c.dim * esz;
+                w.attn = tmp.attn + (size_t)g * Mh * c.dim * esz;
+                w.ff = tmp.ff + (size_t)g * Mh * c.ffn_dim * esz;
+                w.x0 = tmp.x0 ? tmp.x0 + (size_t)g * Mh * c.caption_dim * esz : nullptr;
+                w.partial = tmp.partial + (size_t)g * (pf_full / 2 / 64 * 64);
+                w.logits = tmp.logits + (size_t)g * hr * c.vocab_size;
+                w.tokens = tmp.tokens + (size_t)g * hr;
+                w.counters = tmp.counters + 2 * g;
+                const long long total_rows = (long long)c.n_layer * hr * c.n_head * max_seq;
+                LG_TRY(attn_tma_make_map(w.kmap, w.kcache, total_rows, e->hd));
+                LG_TRY(attn_tma_make_map(w.vmap, w.vcache, total_rows, e->hd));
+                w.have_maps = true;
+                e->sub[g] = w;
+            }
+            e->can_split = true;
+        }
+    }
     return 0;
 }
 
 static int check_ready(lg_engine* e, int rows, int seq) {
     LG_REQUIRE(e && e->finalized, "engine not finalized");
-    LG_REQUIRE(e->ws.base, "workspace not set");
+    LG_REQUIRE(e->full.base, "workspace not set");
+    e->ws = e->full;
     LG_REQUIRE(rows <= e->ws.rows, "rows %d exceed workspace rows %d", rows, e->ws.rows);
     LG_REQUIRE(seq <= e->ws.max_seq, "sequence %d exceeds workspace max_seq %d", seq, e->ws.max_seq);
     LG_REQUIRE(seq <= e->cfg.cls_token_num + e->cfg.block_size, "sequence %d exceeds the RoPE table (%d)", seq,
@@ -455,95 +500,143 @@ static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, 
 
 int lg_generate(lg_engine* e, const void* cond, const float* emb_mask, int B, int T, int S, const lg_sample_cfg* sc,
                 int32_t* out_tokens, float* dbg_logits, const int32_t* teacher, void* stream) {
-    // The loop runs on an engine-owned non-blocking stream forked from / joined to the caller's stream with
+    // The loop runs on engine-owned non-blocking streams forked from / joined to the caller's stream with
     // events: the caller's stream may be the legacy default stream (torch's default), which cannot be captured
     // into a CUDA graph. Semantics for the caller stay "asynchronous on the given stream".
     cudaStream_t caller = (cudaStream_t)stream;
     LG_REQUIRE(e, "lg_generate: null engine");
     if (!e->work) {
         LG_CUDA_OK(cudaStreamCreateWithFlags(&e->work, cudaStreamNonBlocking));
+        LG_CUDA_OK(cudaStreamCreateWithFlags(&e->work2, cudaStreamNonBlocking));
         LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
         LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+        LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
     }
     LG_CUDA_OK(cudaEventRecord(e->ev_fork, caller));
     LG_CUDA_OK(cudaStreamWaitEvent(e->work, e->ev_fork, 0));
+    LG_CUDA_OK(cudaStreamWaitEvent(e->work2, e->ev_fork, 0));
     const int rc = generate_impl(e, cond, emb_mask, B, T, S, sc, out_tokens, dbg_logits, teacher, e->work);
     cudaEventRecord(e->ev_join, e->work);
+    cudaEventRecord(e->ev_join2, e->work2);
     cudaStreamWaitEvent(caller, e->ev_join, 0);
+    cudaStreamWaitEvent(caller, e->ev_join2, 0);
+    if (e->full.base) e->ws = e->full;
     return rc;
 }
 
+namespace {
+// One independent decode chain (a contiguous group of images with its own workspace half, stream and graph).
+struct Chain {
+    Workspace w;
+    cudaStream_t st = nullptr;
+    const void* cond = nullptr;
+    const float* emb_mask = nullptr;
+    int B = 0, R = 0;
+    SampleArgs sa{};
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t per_step = 0;
+};
+}  // namespace
+
 static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, int B, int T, int S,
                          const lg_sample_cfg* sc, int32_t* out_tokens, float* dbg_logits, const int32_t* teacher,
-                         cudaStream_t st) {
+                         cudaStream_t st0) {
     LG_REQUIRE(cond && sc && out_tokens && B > 0 && S > 0, "lg_generate: bad argument");
     const bool use_cfg = sc->cfg_scale > 1.0f;  // generate.py:128
     const int R = use_cfg ? 2 * B : B;
     LG_TRY(check_ready(e, R, T + S));
     LG_REQUIRE(T == e->cfg.cls_token_num, "lg_generate: T=%d must equal cls_token_num=%d", T, e->cfg.cls_token_num);
     if (emb_mask) LG_REQUIRE(e->cfg.model_type == LG_MODEL_T2I, "emb_masks only apply to t2i models");
-    Workspace& ws = e->ws;
-    int* d_pos = ws.counters;
-    int* d_step = ws.counters + 1;
+    const lg_model_cfg& c = e->cfg;
 
-    SampleArgs sa{};
-    sa.logits = ws.logits; sa.B = B; sa.V = e->cfg.vocab_size; sa.mix_cfg = use_cfg;
-    sa.round_bf16 = e->cfg.dtype == LG_DTYPE_BF16;
-    sa.cfg_scale = sc->cfg_scale; sa.cfg_interval = sc->cfg_interval; sa.temperature = sc->temperature;
-    sa.top_k = sc->top_k; sa.top_p = sc->top_p; sa.greedy = sc->greedy; sa.seed = sc->seed;
-    sa.out_seq = out_tokens; sa.seq_stride = S; sa.next_tokens = ws.tokens; sa.teacher = teacher;
-    sa.dbg_logits = dbg_logits;
+    // Dual-chain decode: at large batch every kernel of a decode step is latency-bound (a few microseconds of
+    // dependent load -> compute -> store), so the batch is cut into two independent chains (their own KV-cache half,
+    // stream and CUDA graph) whose kernels interleave on the GPU. Each image's arithmetic is unchanged, so the result
+    // is bit-identical to the single-chain run.
+    const bool split = e->can_split && lg_env_flag("LG_SPLIT", 1) && B % 2 == 0 && R == e->full.rows && R / 2 >= 32 &&
+                       !prof_enabled() && !lg_debug_sync();
+    const int nchains = split ? 2 : 1;
+    Chain ch[2];
+    for (int g = 0; g < nchains; ++g) {
+        Chain& k = ch[g];
+        k.w = split ? e->sub[g] : e->full;
+        k.st = g == 0 ? st0 : e->work2;
+        k.B = B / nchains;
+        k.R = R / nchains;
+        const size_t boff = (size_t)g * k.B;
+        k.cond = c.model_type == LG_MODEL_C2I ? (const void*)((const int32_t*)cond + boff)
+                                              : (const void*)((const char*)cond + boff * T * c.caption_dim * e->esz);
+        k.emb_mask = emb_mask ? emb_mask + boff * T : nullptr;
+        SampleArgs& sa = k.sa;
+        sa.logits = k.w.logits; sa.B = k.B; sa.V = c.vocab_size; sa.mix_cfg = use_cfg;
+        sa.round_bf16 = c.dtype == LG_DTYPE_BF16;
+        sa.cfg_scale = sc->cfg_scale; sa.cfg_interval = sc->cfg_interval; sa.temperature = sc->temperature;
+        sa.top_k = sc->top_k; sa.top_p = sc->top_p; sa.greedy = sc->greedy; sa.seed = sc->seed;
+        sa.row_offset = (int)boff;
+        sa.out_seq = out_tokens + boff * S; sa.seq_stride = S; sa.next_tokens = k.w.tokens;
+        sa.teacher = teacher ? teacher + boff * S : nullptr;
+        sa.dbg_logits = dbg_logits; sa.dbg_batch = B;
+    }
 
-    // ---- prefill (generate.py:167-169)
-    LG_TRY(e->embed_cond(cond, B, R, T, st));
-    LG_TRY(e->forward(R * T, T, PosArg{nullptr, 0}, emb_mask, B, ws.logits, false, st));
-    sa.step = 0; sa.step_dev = nullptr;
-    LG_TRY(launch_sample(sa, st));
-    if (S == 1) return 0;
-
-    // ---- decode loop (generate.py:105-123), device-resident counters
-    LG_TRY(launch_set_counters(d_pos, T, d_step, 1, st));
-    sa.step_dev = d_step;
-    auto body = [&]() -> int {
-        LG_PROF(PC_EMBED_MISC, st, launch_embed(e->tok_emb, ws.tokens, B, R, -1, e->cfg.dim, e->cfg.dtype, ws.h, st));
-        LG_TRY(e->forward(R, 1, PosArg{d_pos, 0}, emb_mask, B, ws.logits, false, st));
-        LG_PROF(PC_SAMPLE, st, launch_sample(sa, st));
-        LG_PROF(PC_EMBED_MISC, st, launch_advance(d_pos, d_step, st));
+    auto body = [&](Chain& k) -> int {
+        e->ws = k.w;
+        int* d_pos = k.w.counters;
+        int* d_step = k.w.counters + 1;
+        LG_PROF(PC_EMBED_MISC, k.st, launch_embed(e->tok_emb, k.w.tokens, k.B, k.R, -1, c.dim, c.dtype, k.w.h, k.st));
+        LG_TRY(e->forward(k.R, 1, PosArg{d_pos, 0}, k.emb_mask, k.B, k.w.logits, false, k.st));
+        LG_PROF(PC_SAMPLE, k.st, launch_sample(k.sa, k.st));
+        LG_PROF(PC_EMBED_MISC, k.st, launch_advance(d_pos, d_step, k.st));
         return 0;
     };
-    LG_TRY(body());  // first decode step runs eagerly (also sets every kernel attribute outside capture)
+
+    // ---- prefill (generate.py:167-169) + first decode step, eagerly, per chain
+    for (int g = 0; g < nchains; ++g) {
+        Chain& k = ch[g];
+        e->ws = k.w;
+        LG_TRY(e->embed_cond(k.cond, k.B, k.R, T, k.st));
+        LG_TRY(e->forward(k.R * T, T, PosArg{nullptr, 0}, k.emb_mask, k.B, k.w.logits, false, k.st));
+        k.sa.step = 0; k.sa.step_dev = nullptr;
+        LG_TRY(launch_sample(k.sa, k.st));
+        if (S == 1) continue;
+        LG_TRY(launch_set_counters(k.w.counters, T, k.w.counters + 1, 1, k.st));
+        k.sa.step_dev = k.w.counters + 1;
+        LG_TRY(body(k));   // first decode step runs eagerly (also sets every kernel attribute outside capture)
+    }
     const int remaining = S - 2;
     if (remaining <= 0) return 0;
     if (!e->use_graph || remaining < 3 || prof_enabled() || lg_debug_sync()) {
-        for (int i = 0; i < remaining; ++i) LG_TRY(body());
+        for (int i = 0; i < remaining; ++i)
+            for (int g = 0; g < nchains; ++g) LG_TRY(body(ch[g]));
         return 0;
     }
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    LG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-    const uint64_t before = g_lg_launches.load();
-    const int rc = body();
-    const uint64_t per_step = g_lg_launches.load() - before;
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (rc < 0) {
-        if (graph) cudaGraphDestroy(graph);
-        return rc;
-    }
-    LG_REQUIRE(ce == cudaSuccess && graph, "stream capture failed: %s", cudaGetErrorString(ce));
-    ce = cudaGraphInstantiate(&exec, graph, 0);
-    if (ce != cudaSuccess) {
-        cudaGraphDestroy(graph);
-        return lg_fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-    }
-    g_lg_launches.fetch_sub(per_step);  // the capture pass launched nothing
+    // ---- decode loop (generate.py:105-123): one captured graph per chain, replayed S-2 times, chains interleaved
     int ret = 0;
-    for (int i = 0; i < remaining; ++i) {
-        ce = cudaGraphLaunch(exec, st);
-        if (ce != cudaSuccess) { ret = lg_fail("cudaGraphLaunch failed: %s", cudaGetErrorString(ce)); break; }
-        g_lg_launches.fetch_add(per_step);
+    for (int g = 0; g < nchains && ret == 0; ++g) {
+        Chain& k = ch[g];
+        cudaError_t ce = cudaStreamBeginCapture(k.st, cudaStreamCaptureModeRelaxed);
+        if (ce != cudaSuccess) { ret = lg_fail("cudaStreamBeginCapture failed: %s", cudaGetErrorString(ce)); break; }
+        const uint64_t before = g_lg_launches.load();
+        const int rc = body(k);
+        k.per_step = g_lg_launches.load() - before;
+        ce = cudaStreamEndCapture(k.st, &k.graph);
+        g_lg_launches.fetch_sub(k.per_step);  // the capture pass launched nothing
+        if (rc < 0) { ret = rc; break; }
+        if (ce != cudaSuccess || !k.graph) { ret = lg_fail("stream capture failed: %s", cudaGetErrorString(ce)); break; }
+        ce = cudaGraphInstantiate(&k.exec, k.graph, 0);
+        if (ce != cudaSuccess) { ret = lg_fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); break; }
     }
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
+    for (int i = 0; i < remaining && ret == 0; ++i) {
+        for (int g = 0; g < nchains; ++g) {
+            const cudaError_t ce = cudaGraphLaunch(ch[g].exec, ch[g].st);
+            if (ce != cudaSuccess) { ret = lg_fail("cudaGraphLaunch failed: %s", cudaGetErrorString(ce)); break; }
+            g_lg_launches.fetch_add(ch[g].per_step);
+        }
+    }
+    for (int g = 0; g < nchains; ++g) {
+        if (ch[g].exec) cudaGraphExecDestroy(ch[g].exec);
+        if (ch[g].graph) cudaGraphDestroy(ch[g].graph);
+    }
     return ret;
 }
 

@@ -26,7 +26,8 @@ struct SampleArgs {
     int seq_stride;
     int32_t* next_tokens;  // [B] or null: token fed to the next decode step
     const int32_t* teacher;// [B, seq_stride] or null: teacher-forced next token
-    float* dbg_logits;     // [S, B, V] or null: mixed logits before temperature
+    float* dbg_logits;     // [S, dbg_batch, V] or null: mixed logits before temperature (row = row_offset + b)
+    int dbg_batch;         // total images in the dbg buffer (0 -> B)
 };
 int launch_sample(const SampleArgs& a, cudaStream_t st);
 

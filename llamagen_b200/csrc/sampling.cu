@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
     const float* lc = a.logits + (size_t)b * V;
     const float* lu = a.logits + (size_t)(B + b) * V;
     const float tdiv = fmaxf(a.temperature, 1e-5f);
-    float* dbg = a.dbg_logits ? a.dbg_logits + ((size_t)step * B + b) * V : nullptr;
+    const int dbgB = a.dbg_batch > 0 ? a.dbg_batch : B;
+    float* dbg = a.dbg_logits ? a.dbg_logits + ((size_t)step * dbgB + a.row_offset + b) * V : nullptr;
 
     for (int v = tid; v < V; v += kSampleThreads) {
         float c = lc[v];
