@@ -39,6 +39,7 @@ struct TcArgs {
     int kblocks_per_split;
     int tmem_cols;        // power of two >= max(32, rpad)
     int stages;           // smem ring depth (<= kMaxStages), sized to fit 227 KB
+    int swap;             // 1: weights are the UMMA A operand (TMEM lane = feature); 0: activations are A (TMEM lane = row)
     float* partial;       // [ksplit][M][N]
     const char* pf0; unsigned long long pfb0;   // next GEMM's weights to pull into L2 (see GemmNext)
     const char* pf1; unsigned long long pfb1;
@@ -61,7 +62,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // stage s: A tile at s*stage_bytes (1024-aligned), B tile right after
     const int b_tile_bytes = a.rpad * kBlockK * 2;
-    const int stage_bytes = kATileBytes + ((b_tile_bytes + 1023) / 1024) * 1024;
+    // activations tile: rpad rows are loaded; when it is the UMMA A operand (M = 128) the full 128-row slot is reserved
+    const int stage_bytes = kATileBytes + (a.swap ? ((b_tile_bytes + 1023) / 1024) * 1024 : kATileBytes);
     uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int kStages = a.stages;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStages * stage_bytes);
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         lg_pdl_wait();
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = make_idesc(a.rpad);
+        const uint32_t idesc = make_idesc(a.swap ? a.rpad : kBlockN);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % kStages;
             const uint32_t ph = (uint32_t)((i / kStages) & 1);
@@ -154,8 +156,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (i == nkb - 1 && lane == 0) TC_TRACE(4);
             if (elect_one()) {
                 const uint32_t sa = smem_u32(tiles + s * stage_bytes);
-                const uint64_t adesc = make_desc_sw128(sa);
-                const uint64_t bdesc = make_desc_sw128(sa + kATileBytes);
+                const uint64_t wdesc = make_desc_sw128(sa);
+                const uint64_t xdesc = make_desc_sw128(sa + kATileBytes);
+                const uint64_t adesc = a.swap ? wdesc : xdesc, bdesc = a.swap ? xdesc : wdesc;
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (addr >> 4) field
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
     }
     // ---------------------------------------------------------------------- drain: TMEM -> registers -> fp32 slab
-    {
+    if (a.swap) {
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int half = warp >> 2;                   // which half of the columns (activation rows) it drains
         const int n = n0 + q * 32 + lane;
@@ -199,6 +202,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
         } else if (n < a.N) {
             for (int r = c_begin; r < min(c_end, a.M); ++r) out[(size_t)r * a.N + n] = 0.f;
+        }
+    } else {
+        // activations are the A operand: TMEM lane = row r, columns = 128 features -> 64-byte vector stores per thread
+        const int q = warp & 3, half = warp >> 2;
+        const int r = q * 32 + lane;
+        const int c_begin = half * (kBlockN / 2), c_end = c_begin + kBlockN / 2;
+        float* out = a.partial + (size_t)ks * a.M * a.N + (size_t)r * a.N + n0;
+        if (nkb > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (threadIdx.x == 64) TC_TRACE(5);
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (r < a.M && n0 + c0 + 16 <= a.N) {
+                    float4* p4 = reinterpret_cast<float4*>(out + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        p4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                            __uint_as_float(v[4 * j + 3]));
+                } else if (r < a.M) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + c0 + j < a.N) out[c0 + j] = __uint_as_float(v[j]);
+                }
+            }
+        } else if (r < a.M) {
+            for (int c = c_begin; c < c_end; ++c)
+                if (n0 + c < a.N) out[c] = 0.f;
         }
     }
     if (threadIdx.x == 64) TC_TRACE(6);
@@ -289,8 +321,11 @@ int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int 
     const int ks = gemm_tc_ksplit(M, N, K);
     const int kb = cdiv(K, kBlockK);
     a.kblocks_per_split = cdiv(kb, ks);
+    // rows-as-lanes (swap = 0, 64-byte vector stores per thread) was measured SLOWER than features-as-lanes on B200:
+    // each warp store then touches 32 different 128-byte lines (drain 2.8-3.2 us vs 1.1 us), so it stays opt-in.
+    a.swap = (lg_env_flag("LG_TC_NOSWAP", 0) && M > 64 && M <= kBlockN) ? 0 : 1;
     a.tmem_cols = 32;
-    while (a.tmem_cols < a.rpad) a.tmem_cols *= 2;
+    while (a.tmem_cols < (a.swap ? a.rpad : kBlockN)) a.tmem_cols *= 2;
     a.partial = partial;
     if (ksplit_out) *ksplit_out = ks;
 
@@ -300,7 +335,7 @@ int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int 
     LG_TRY(tma::make_map_2d(&mx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, (uint32_t)a.rpad, kBlockK));
 
     const int b_tile_bytes = a.rpad * kBlockK * 2;
-    const int stage_bytes = kATileBytes + ((b_tile_bytes + 1023) / 1024) * 1024;
+    const int stage_bytes = kATileBytes + (a.swap ? ((b_tile_bytes + 1023) / 1024) * 1024 : kATileBytes);
     a.stages = std::min(std::min(kMaxStages, lg_env_flag("LG_TC_STAGES", kMaxStages)), (int)((225 * 1024 - 1024) / stage_bytes));
     a.stages = std::min(a.stages, std::max(2, a.kblocks_per_split));   // never more stages than k-blocks
     a.trace = g_tc_trace;
