@@ -1,0 +1,46 @@
+"""Two-stage sampling pipeline: AR generation of batch i+1 overlaps the VQ decode of batch i.
+
+The AR decode loop is latency-bound (≈ 220 short dependent kernels per token) and leaves most SMs idle, while the
+VQ decode is a dense tensor-core burst; running them on two streams lets the decode fill the idle machine.
+This is the steady-state loop of the reference's DDP sampler (sample_c2i_ddp.py:128-149), reorganised:
+    for labels in batches: tokens = generate(labels); pixels = decode_code(tokens); emit(pixels)
+"""
+from __future__ import annotations
+
+import torch
+
+from .generate import generate
+
+
+class SamplePipeline:
+    def __init__(self, gpt_model, vq_model, codebook_embed_dim: int = 8, **sampling_kwargs):
+        self.gpt, self.vq = gpt_model, vq_model
+        self.kw = sampling_kwargs
+        self.embed_dim = codebook_embed_dim
+        dev = gpt_model.tok_embeddings.weight.device
+        self.dev = dev
+        self.decode_stream = torch.cuda.Stream(device=dev)
+        self._last = None
+
+    def submit(self, cond, grid: int, to_uint8_host=None):
+        """Enqueue generate() on the current stream and decode_code() on the decode stream. Returns the pixel tensor
+        (fp32 NCHW); it is complete once `self.decode_stream` (or `wait()`) has been synchronised. When
+        `to_uint8_host` (a pinned uint8 [B,H,W,3] tensor) is given, the clamp/convert of sample_c2i_ddp.py:143 and the
+        device-to-host copy are enqueued behind the decode as well."""
+        main = torch.cuda.current_stream(self.dev)
+        tokens = generate(self.gpt, cond, grid * grid, **self.kw)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.decode_stream.wait_event(ready)
+        tokens.record_stream(self.decode_stream)
+        with torch.cuda.stream(self.decode_stream):
+            pixels = self.vq.decode_code(tokens, [tokens.shape[0], self.embed_dim, grid, grid])
+            if to_uint8_host is not None:
+                u8 = torch.clamp(127.5 * pixels + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+                to_uint8_host.copy_(u8, non_blocking=True)
+        self._last = pixels
+        return pixels
+
+    def wait(self):
+        """Make the current stream wait for every decode submitted so far."""
+        torch.cuda.current_stream(self.dev).wait_stream(self.decode_stream)
