@@ -11,7 +11,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
                     c_void_p)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libllamagen_b200.so")
+LIB_PATH = os.environ.get("LG_LIB_PATH") or os.path.join(HERE, "lib", "libllamagen_b200.so")
 
 LG_DTYPE_F32, LG_DTYPE_BF16 = 0, 1
 LG_MODEL_C2I, LG_MODEL_T2I = 0, 1

@@ -14,8 +14,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT_DIR = os.path.join(HERE, "lib")
+# A/B builds: LG_NVCC_DEFS="-DLG_ATTN_KC=48" LG_LIB_DIR=lib_kc48 python -m llamagen_b200.build ; run with LG_LIB_PATH=...
+OUT_DIR = os.path.join(HERE, os.environ.get("LG_LIB_DIR", "lib"))
 LIB = os.path.join(OUT_DIR, "libllamagen_b200.so")
+EXTRA_DEFS = os.environ.get("LG_NVCC_DEFS", "").split()
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -33,7 +35,7 @@ def _digest() -> str:
             h.update(f.encode())
             h.update(open(os.path.join(CSRC, f), "rb").read())
     h.update(open(os.path.join(HERE, "..", "include", "llamagen_b200.h"), "rb").read())
-    h.update(" ".join(ARCH + CFLAGS).encode())
+    h.update(" ".join(ARCH + CFLAGS + EXTRA_DEFS).encode())
     return h.hexdigest()
 
 
@@ -49,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [NVCC, *ARCH, *CFLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *ARCH, *CFLAGS, *EXTRA_DEFS, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OUT_DIR, src.replace(".cu", ".ptxas.log"))
         with open(log, "w") as f:

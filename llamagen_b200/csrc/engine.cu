@@ -7,6 +7,7 @@
 // The decode loop never leaves the device: sampled tokens, the position and the step counter live in
 // HBM, so one captured CUDA graph of a decode step is replayed S-2 times with no host round trip.
 #include "kernels.cuh"
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -135,17 +136,18 @@ struct lg_engine {
     const float* freqs = nullptr;
     bool finalized = false;
     Workspace ws;                         // ACTIVE workspace (full, or one of the two halves while a group is issued)
-    Workspace full, sub[2];               // sub[g]: rows/2 each, carved INSIDE the regions of `full` (dual-chain decode)
-    bool can_split = false;
+    static constexpr int kMaxChains = 4;
+    Workspace full, sub[kMaxChains];      // sub[g]: rows/n_sub each, carved INSIDE the regions of `full` (multi-chain decode)
+    int n_sub = 0;                        // 0: no split available
     bool use_graph = true;
-    cudaStream_t work = nullptr, work2 = nullptr;   // engine-owned streams the generate loop (and its graphs) run on
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    cudaStream_t works[kMaxChains] = {nullptr, nullptr, nullptr, nullptr};   // engine-owned streams (one per chain)
+    cudaEvent_t ev_fork = nullptr, ev_joins[kMaxChains] = {nullptr, nullptr, nullptr, nullptr};
     ~lg_engine() {
-        if (work) cudaStreamDestroy(work);
-        if (work2) cudaStreamDestroy(work2);
+        for (int i = 0; i < kMaxChains; ++i) {
+            if (works[i]) cudaStreamDestroy(works[i]);
+            if (ev_joins[i]) cudaEventDestroy(ev_joins[i]);
+        }
         if (ev_fork) cudaEventDestroy(ev_fork);
-        if (ev_join) cudaEventDestroy(ev_join);
-        if (ev_join2) cudaEventDestroy(ev_join2);
     }
 
     size_t carve(Workspace& o, char* base, int rows, int max_seq) const;
@@ -404,19 +406,23 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
     }
     e->full = tmp;
     e->ws = tmp;
-    // Two half-batch workspaces inside the same memory (every region scales with rows, so each half takes one half
-    // of every region; the K/V halves stay inside the zero-initialised cache regions).
-    e->can_split = false;
-    if (rows % 2 == 0 && rows / 2 >= 32 && e->cfg.dtype == LG_DTYPE_BF16 && tmp.have_maps) {
+    // n equal sub-batch workspaces inside the same memory (every region scales with rows, so chain g takes the g-th
+    // 1/n of every region; the K/V parts stay inside the zero-initialised cache regions).
+    e->n_sub = 0;
+    int n = lg_env_flag("LG_SPLIT", 2);
+    if (n > lg_engine::kMaxChains) n = lg_engine::kMaxChains;
+    while (n >= 2 && (rows % n != 0 || (rows / n) % 2 != 0 || rows / n < 16)) --n;
+    if (n >= 2 && e->cfg.dtype == LG_DTYPE_BF16 && tmp.have_maps) {
         const lg_model_cfg& c = e->cfg;
-        const int hr = rows / 2;
+        const int hr = rows / n;
         const int Tc = c.model_type == LG_MODEL_T2I ? c.cls_token_num : 1;
         const size_t Mh = (size_t)hr * Tc, esz = e->esz;
         Workspace probe;
         e->carve(probe, nullptr, hr, max_seq);
-        const size_t pf_full = tmp.partial_floats, pf_half = probe.partial_floats;
-        if (pf_half <= pf_full / 2 / 64 * 64) {
-            for (int g = 0; g < 2; ++g) {
+        const size_t pf_full = tmp.partial_floats, pf_part = probe.partial_floats;
+        const size_t pf_slot = pf_full / n / 64 * 64;
+        if (pf_part <= pf_slot) {
+            for (int g = 0; g < n; ++g) {
                 Workspace w = tmp;
                 w.rows = hr;
                 w.layer_cache_bytes = (size_t)hr * c.n_head * max_seq * e->hd * esz;
@@ -428,7 +434,7 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
                 w.attn = tmp.attn + (size_t)g * Mh * c.dim * esz;
                 w.ff = tmp.ff + (size_t)g * Mh * c.ffn_dim * esz;
                 w.x0 = tmp.x0 ? tmp.x0 + (size_t)g * Mh * c.caption_dim * esz : nullptr;
-                w.partial = tmp.partial + (size_t)g * (pf_full / 2 / 64 * 64);
+                w.partial = tmp.partial + (size_t)g * pf_slot;
                 w.logits = tmp.logits + (size_t)g * hr * c.vocab_size;
                 w.tokens = tmp.tokens + (size_t)g * hr;
                 w.counters = tmp.counters + 2 * g;
@@ -438,7 +444,7 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
                 w.have_maps = true;
                 e->sub[g] = w;
             }
-            e->can_split = true;
+            e->n_sub = n;
         }
     }
     return 0;
@@ -505,21 +511,20 @@ int lg_generate(lg_engine* e, const void* cond, const float* emb_mask, int B, in
     // into a CUDA graph. Semantics for the caller stay "asynchronous on the given stream".
     cudaStream_t caller = (cudaStream_t)stream;
     LG_REQUIRE(e, "lg_generate: null engine");
-    if (!e->work) {
-        LG_CUDA_OK(cudaStreamCreateWithFlags(&e->work, cudaStreamNonBlocking));
-        LG_CUDA_OK(cudaStreamCreateWithFlags(&e->work2, cudaStreamNonBlocking));
+    if (!e->works[0]) {
+        for (int i = 0; i < lg_engine::kMaxChains; ++i) {
+            LG_CUDA_OK(cudaStreamCreateWithFlags(&e->works[i], cudaStreamNonBlocking));
+            LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_joins[i], cudaEventDisableTiming));
+        }
         LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-        LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-        LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
     }
     LG_CUDA_OK(cudaEventRecord(e->ev_fork, caller));
-    LG_CUDA_OK(cudaStreamWaitEvent(e->work, e->ev_fork, 0));
-    LG_CUDA_OK(cudaStreamWaitEvent(e->work2, e->ev_fork, 0));
-    const int rc = generate_impl(e, cond, emb_mask, B, T, S, sc, out_tokens, dbg_logits, teacher, e->work);
-    cudaEventRecord(e->ev_join, e->work);
-    cudaEventRecord(e->ev_join2, e->work2);
-    cudaStreamWaitEvent(caller, e->ev_join, 0);
-    cudaStreamWaitEvent(caller, e->ev_join2, 0);
+    for (int i = 0; i < lg_engine::kMaxChains; ++i) LG_CUDA_OK(cudaStreamWaitEvent(e->works[i], e->ev_fork, 0));
+    const int rc = generate_impl(e, cond, emb_mask, B, T, S, sc, out_tokens, dbg_logits, teacher, e->works[0]);
+    for (int i = 0; i < lg_engine::kMaxChains; ++i) {
+        cudaEventRecord(e->ev_joins[i], e->works[i]);
+        cudaStreamWaitEvent(caller, e->ev_joins[i], 0);
+    }
     if (e->full.base) e->ws = e->full;
     return rc;
 }
@@ -550,18 +555,18 @@ static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, 
     if (emb_mask) LG_REQUIRE(e->cfg.model_type == LG_MODEL_T2I, "emb_masks only apply to t2i models");
     const lg_model_cfg& c = e->cfg;
 
-    // Dual-chain decode: at large batch every kernel of a decode step is latency-bound (a few microseconds of
-    // dependent load -> compute -> store), so the batch is cut into two independent chains (their own KV-cache half,
+    // Multi-chain decode: at large batch every kernel of a decode step is latency-bound (a few microseconds of
+    // dependent load -> compute -> store), so the batch is cut into LG_SPLIT (default 2, max 4) independent chains (their own KV-cache half,
     // stream and CUDA graph) whose kernels interleave on the GPU. Each image's arithmetic is unchanged, so the result
     // is bit-identical to the single-chain run.
-    const bool split = e->can_split && lg_env_flag("LG_SPLIT", 1) && B % 2 == 0 && R == e->full.rows && R / 2 >= 32 &&
+    const bool split = e->n_sub >= 2 && lg_env_flag("LG_SPLIT", 2) >= 2 && R == e->full.rows && B % e->n_sub == 0 &&
                        !prof_enabled() && !lg_debug_sync();
-    const int nchains = split ? 2 : 1;
-    Chain ch[2];
+    const int nchains = split ? e->n_sub : 1;
+    Chain ch[lg_engine::kMaxChains];
     for (int g = 0; g < nchains; ++g) {
         Chain& k = ch[g];
         k.w = split ? e->sub[g] : e->full;
-        k.st = g == 0 ? st0 : e->work2;
+        k.st = g == 0 ? st0 : e->works[g];
         k.B = B / nchains;
         k.R = R / nchains;
         const size_t boff = (size_t)g * k.B;
@@ -610,28 +615,52 @@ static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, 
             for (int g = 0; g < nchains; ++g) LG_TRY(body(ch[g]));
         return 0;
     }
-    // ---- decode loop (generate.py:105-123): one captured graph per chain, replayed S-2 times, chains interleaved
+    // ---- decode loop (generate.py:105-123): per chain one captured graph of `unroll` consecutive steps (the loop
+    // state is device-resident, so every step has identical kernel arguments), replayed, chains interleaved; the
+    // remainder runs through a second single-step graph. LG_GRAPH_UNROLL > 1 was measured neutral on B200 (the gap
+    // between graph launches is already hidden by the second chain), so the default is one step per graph.
     int ret = 0;
-    for (int g = 0; g < nchains && ret == 0; ++g) {
-        Chain& k = ch[g];
+    const int unroll = std::max(1, std::min(lg_env_flag("LG_GRAPH_UNROLL", 1), remaining));
+    auto capture = [&](Chain& k, int nsteps, cudaGraph_t* graph, cudaGraphExec_t* exec, uint64_t* launches) -> int {
         cudaError_t ce = cudaStreamBeginCapture(k.st, cudaStreamCaptureModeRelaxed);
-        if (ce != cudaSuccess) { ret = lg_fail("cudaStreamBeginCapture failed: %s", cudaGetErrorString(ce)); break; }
+        if (ce != cudaSuccess) return lg_fail("cudaStreamBeginCapture failed: %s", cudaGetErrorString(ce));
         const uint64_t before = g_lg_launches.load();
-        const int rc = body(k);
-        k.per_step = g_lg_launches.load() - before;
-        ce = cudaStreamEndCapture(k.st, &k.graph);
-        g_lg_launches.fetch_sub(k.per_step);  // the capture pass launched nothing
-        if (rc < 0) { ret = rc; break; }
-        if (ce != cudaSuccess || !k.graph) { ret = lg_fail("stream capture failed: %s", cudaGetErrorString(ce)); break; }
-        ce = cudaGraphInstantiate(&k.exec, k.graph, 0);
-        if (ce != cudaSuccess) { ret = lg_fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); break; }
+        int rc = 0;
+        for (int i = 0; i < nsteps && rc == 0; ++i) rc = body(k);
+        *launches = g_lg_launches.load() - before;
+        ce = cudaStreamEndCapture(k.st, graph);
+        g_lg_launches.fetch_sub(*launches);  // the capture pass launched nothing
+        if (rc < 0) return rc;
+        if (ce != cudaSuccess || !*graph) return lg_fail("stream capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(exec, *graph, 0);
+        if (ce != cudaSuccess) return lg_fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+        return 0;
+    };
+    cudaGraph_t g1[lg_engine::kMaxChains] = {nullptr, nullptr, nullptr, nullptr};
+    cudaGraphExec_t e1[lg_engine::kMaxChains] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t l1[lg_engine::kMaxChains] = {0, 0, 0, 0};
+    const int nbig = remaining / unroll, nsmall = remaining - nbig * unroll;
+    for (int g = 0; g < nchains && ret == 0; ++g) {
+        ret = capture(ch[g], unroll, &ch[g].graph, &ch[g].exec, &ch[g].per_step);
+        if (ret == 0 && nsmall > 0 && unroll > 1) ret = capture(ch[g], 1, &g1[g], &e1[g], &l1[g]);
     }
-    for (int i = 0; i < remaining && ret == 0; ++i) {
+    for (int i = 0; i < nbig && ret == 0; ++i) {
         for (int g = 0; g < nchains; ++g) {
             const cudaError_t ce = cudaGraphLaunch(ch[g].exec, ch[g].st);
             if (ce != cudaSuccess) { ret = lg_fail("cudaGraphLaunch failed: %s", cudaGetErrorString(ce)); break; }
             g_lg_launches.fetch_add(ch[g].per_step);
         }
+    }
+    for (int i = 0; i < nsmall && ret == 0 && unroll > 1; ++i) {
+        for (int g = 0; g < nchains; ++g) {
+            const cudaError_t ce = cudaGraphLaunch(e1[g], ch[g].st);
+            if (ce != cudaSuccess) { ret = lg_fail("cudaGraphLaunch failed: %s", cudaGetErrorString(ce)); break; }
+            g_lg_launches.fetch_add(l1[g]);
+        }
+    }
+    for (int g = 0; g < nchains; ++g) {
+        if (e1[g]) cudaGraphExecDestroy(e1[g]);
+        if (g1[g]) cudaGraphDestroy(g1[g]);
     }
     for (int g = 0; g < nchains; ++g) {
         if (ch[g].exec) cudaGraphExecDestroy(ch[g].exec);

@@ -40,12 +40,20 @@ for e in evs:
     name = name.split("(")[0][:70]
     agg[name][0] += 1
     agg[name][1] += e.time_range.end - e.time_range.start
+# critical-path view (meaningful with PDL on, where kernels start early and wait): time between consecutive kernel ENDS
+ends = sorted(evs, key=lambda e: e.time_range.end)
+cp = collections.defaultdict(lambda: [0, 0.0])
+for prev, cur in zip(ends[:-1], ends[1:]):
+    nm = cur.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:70]
+    cp[nm][0] += 1
+    cp[nm][1] += cur.time_range.end - prev.time_range.end
 busy = sum(v[1] for v in agg.values())
 span = evs[-1].time_range.end - evs[0].time_range.start
 gaps = [max(0, b.time_range.start - a.time_range.end) for a, b in zip(evs[:-1], evs[1:])]
 gaps_sorted = sorted(gaps)
 res = {"kernels": len(evs), "span_us": span, "busy_us": busy, "idle_us": span - busy,
        "median_gap_us": gaps_sorted[len(gaps) // 2], "p90_gap_us": gaps_sorted[int(len(gaps) * 0.9)],
+       "end_to_end_delta": {k: {"n": v[0], "total_us": round(v[1], 1), "avg_us": round(v[1] / v[0], 2)} for k, v in sorted(cp.items(), key=lambda kv: -kv[1][1])},
        "per_kernel": {k: {"n": v[0], "total_us": round(v[1], 1), "avg_us": round(v[1] / v[0], 2), "share_of_span": round(v[1] / span, 4)}
                       for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}}
 print(json.dumps(res, indent=1))
