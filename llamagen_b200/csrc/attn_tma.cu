@@ -42,25 +42,36 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 struct AttnTmaArgs {
-    const bf16* q;     // [R, D]
+    const bf16* q;     // [R, D] (unfused path)
     bf16* out;         // [R, D]
     int R, H, maxS;
     const int* pos_dev; int pos_value;
     long long row_base;          // first cache row of this layer inside the tensor maps
     const float* emb_mask; int B, Tc;
     float scale;
+    // fused QKV epilogue (FUSED kernels): split-K slabs of the QKV GEMM, RoPE table, this layer's cache bases
+    const float* partial; int ksplit;
+    const float* freqs;
+    bf16* kcache; bf16* vcache;
 };
 
-template <int HD>
+// FUSED = true: the kernel also IS the QKV epilogue of gpt.py:214-230 for its (row, head): it reduces the split-K
+// slabs of the QKV GEMM for its 3*hd columns, applies RoPE to q and k, writes the new K/V row into the cache
+// (for future steps) and attends to it straight from shared memory. Every TMA load then only touches rows written
+// in EARLIER steps, so the whole KV stream is requested before the programmatic-dependency wait and overlaps the
+// QKV GEMM; one dependent kernel per layer disappears.
+template <int HD, bool FUSED>
 __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
                                                                const __grid_constant__ CUtensorMap vmap, AttnTmaArgs a) {
     constexpr int NSUB = HD / 64;                 // 128-byte-wide sub-tiles per row
-    constexpr int SUB_BYTES = kKC * 128;          // one [64 keys][64 dims] bf16 sub-tile
+    constexpr int SUB_BYTES = kKC * 128;          // one [kKC keys][64 dims] bf16 sub-tile
     constexpr int TILE_BYTES = NSUB * SUB_BYTES;  // K (or V) of one stage
+    constexpr int NSLOT = kWarps + (FUSED ? 1 : 0);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStagesA * 2 * TILE_BYTES);
-    float* merge = reinterpret_cast<float*>(full_bar + kStagesA);   // [kWarps][HD + 2]
+    float* merge = reinterpret_cast<float*>(full_bar + kStagesA);            // [NSLOT][HD + 2]
+    bf16* qbuf = reinterpret_cast<bf16*>(merge + NSLOT * (HD + 2));            // [3][HD]: q, k_new, v_new (FUSED)
 
     const int h = blockIdx.x, r = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
@@ -74,12 +85,10 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
         fence_barrier_init();
     }
     __syncthreads();
-    // Programmatic dependent launch: only the LAST chunk (the one holding this step's key, written by the
-    // immediately preceding RoPE/KV-write kernel) and q depend on the predecessor. Every older key row and the
-    // position counter were produced at least one kernel earlier, so their TMA loads are issued before the
-    // dependency wait and overlap the predecessor's execution.
+    // Programmatic dependent launch: the position counter and every key row of EARLIER steps were produced at least
+    // one kernel before the predecessor, so their TMA loads are issued before the dependency wait.
     const int qpos = (a.pos_dev ? *a.pos_dev : 0) + a.pos_value;
-    const int nkeys = qpos + 1;
+    const int nkeys = FUSED ? qpos : qpos + 1;      // keys streamed from the cache (FUSED: the new key stays on chip)
     const int nchunks = (nkeys + kKC - 1) / kKC;
 
     auto issue = [&](int ci) {
@@ -96,19 +105,59 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
     const int npro = min(kStagesA, nchunks);
     if (threadIdx.x == 0)
         for (int ci = 0; ci < npro; ++ci)
-            if (ci != nchunks - 1) issue(ci);
+            if (FUSED || ci != nchunks - 1) issue(ci);
     lg_pdl_sync();
-    if (threadIdx.x == 0 && nchunks - 1 < npro) issue(nchunks - 1);
+    if (!FUSED && threadIdx.x == 0 && nchunks - 1 < npro && nchunks > 0) issue(nchunks - 1);
 
-    // q as the A operand of m16n8k16: only MMA row 0 (lanes with g == 0) is real, the other 15 rows are zero
     uint32_t qa[HD / 16][2];
-    const bf16* qp = a.q + (size_t)r * D + (size_t)h * HD;
+    if (FUSED) {
+        // ---- QKV epilogue for this (row, head): slab reduce -> dtype rounding -> RoPE -> cache write / smem
+        if (threadIdx.x < 3 * HD / 4) {
+            const int sec = threadIdx.x / (HD / 4), e = (threadIdx.x % (HD / 4)) * 4;
+            const size_t N3 = (size_t)3 * D, slab = (size_t)a.R * N3;
+            const float* p = a.partial + (size_t)r * N3 + (size_t)sec * D + (size_t)h * HD + e;
+            float4 sv = *reinterpret_cast<const float4*>(p);
+            for (int k = 1; k < a.ksplit; ++k) {
+                const float4 t = *reinterpret_cast<const float4*>(p + (size_t)k * slab);
+                sv.x += t.x; sv.y += t.y; sv.z += t.z; sv.w += t.w;
+            }
+            float x0 = round_bf16(sv.x), x1 = round_bf16(sv.y), x2 = round_bf16(sv.z), x3 = round_bf16(sv.w);
+            if (sec < 2) {   // apply_rotary_emb (gpt.py:420-430): adjacent pairs, fp32, separate roundings
+                const float4 cs = *reinterpret_cast<const float4*>(a.freqs + ((size_t)qpos * (HD / 2) + (e >> 1)) * 2);
+                const float y0 = __fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y));
+                const float y1 = __fadd_rn(__fmul_rn(x1, cs.x), __fmul_rn(x0, cs.y));
+                const float y2 = __fsub_rn(__fmul_rn(x2, cs.z), __fmul_rn(x3, cs.w));
+                const float y3 = __fadd_rn(__fmul_rn(x3, cs.z), __fmul_rn(x2, cs.w));
+                x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+            }
+            uint2 pk;
+            pk.x = pack_bf16(x0, x1);
+            pk.y = pack_bf16(x2, x3);
+            *reinterpret_cast<uint2*>(qbuf + sec * HD + e) = pk;
+            if (sec > 0) {
+                bf16* cache = sec == 1 ? a.kcache : a.vcache;
+                *reinterpret_cast<uint2*>(cache + (((size_t)r * a.H + h) * a.maxS + qpos) * HD + e) = pk;
+            }
+        }
+        __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < HD / 16; ++kk) {
-        qa[kk][0] = 0; qa[kk][1] = 0;
-        if (g == 0) {
-            qa[kk][0] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + tg * 2);
-            qa[kk][1] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + 8 + tg * 2);
+        for (int kk = 0; kk < HD / 16; ++kk) {
+            qa[kk][0] = 0; qa[kk][1] = 0;
+            if (g == 0) {
+                qa[kk][0] = *reinterpret_cast<const uint32_t*>(qbuf + kk * 16 + tg * 2);
+                qa[kk][1] = *reinterpret_cast<const uint32_t*>(qbuf + kk * 16 + 8 + tg * 2);
+            }
+        }
+    } else {
+        // q as the A operand of m16n8k16: only MMA row 0 (lanes with g == 0) is real, the other 15 rows are zero
+        const bf16* qp = a.q + (size_t)r * D + (size_t)h * HD;
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+            qa[kk][0] = 0; qa[kk][1] = 0;
+            if (g == 0) {
+                qa[kk][0] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + tg * 2);
+                qa[kk][1] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + 8 + tg * 2);
+            }
         }
     }
     const float* mrow = a.emb_mask ? a.emb_mask + (size_t)(r % a.B) * a.Tc : nullptr;
@@ -182,7 +231,7 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
         if (threadIdx.x == 0 && ci + kStagesA < nchunks) issue(ci + kStagesA);
     }
 
-    // ---- merge the four warps (each saw a disjoint key subset)
+    // ---- merge the warps (each saw a disjoint key subset) and, when FUSED, the new key held in shared memory
     float* wrow = merge + warp * (HD + 2);
     if (g == 0) {
 #pragma unroll
@@ -192,15 +241,31 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
         }
         if (tg == 0) { wrow[HD] = mx; wrow[HD + 1] = l; }
     }
+    if (FUSED && warp == 0) {
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < HD / 32; ++i) {
+            const int e = lane * (HD / 32) + i;
+            dot = fmaf(__bfloat162float(qbuf[e]), __bfloat162float(qbuf[HD + e]), dot);
+        }
+        dot = warp_sum(dot);
+        float* crow = merge + kWarps * (HD + 2);
+#pragma unroll
+        for (int i = 0; i < HD / 32; ++i) {
+            const int e = lane * (HD / 32) + i;
+            crow[e] = __bfloat162float(qbuf[2 * HD + e]);
+        }
+        if (lane == 0) { crow[HD] = dot * a.scale; crow[HD + 1] = 1.f; }
+    }
     __syncthreads();
     bf16* op = a.out + (size_t)r * D + (size_t)h * HD;
     for (int e = threadIdx.x; e < HD; e += blockDim.x) {
         float M_ = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) M_ = fmaxf(M_, merge[w * (HD + 2) + HD]);
+        for (int w = 0; w < NSLOT; ++w) M_ = fmaxf(M_, merge[w * (HD + 2) + HD]);
         float L = 0.f, O = 0.f;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
+        for (int w = 0; w < NSLOT; ++w) {
             const float mw = merge[w * (HD + 2) + HD];
             const float c = mw == -INFINITY ? 0.f : __expf(mw - M_);
             L += merge[w * (HD + 2) + HD + 1] * c;
@@ -391,17 +456,18 @@ int launch_v2(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnTmaArg
     return 0;
 }
 
-template <int HD>
+template <int HD, bool FUSED>
 int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnTmaArgs& a, cudaStream_t st) {
     constexpr int TILE_BYTES = (HD / 64) * kKC * 128;
-    const size_t smem = 1024 + (size_t)kStagesA * 2 * TILE_BYTES + kStagesA * sizeof(uint64_t) + kWarps * (HD + 2) * sizeof(float);
+    const size_t smem = 1024 + (size_t)kStagesA * 2 * TILE_BYTES + kStagesA * sizeof(uint64_t) +
+                        (kWarps + 1) * (HD + 2) * sizeof(float) + 3 * HD * sizeof(bf16) + 16;
     static bool attr = false;
     if (!attr) {
-        LG_CUDA_OK(cudaFuncSetAttribute(attn_tma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LG_CUDA_OK(cudaFuncSetAttribute(attn_tma_kernel<HD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     dim3 grid(a.H, a.R);
-    (void)lg_launch(attn_tma_kernel<HD>, dim3(grid), dim3(kWarps * 32), smem, st, kmap, vmap, a);
+    (void)lg_launch(attn_tma_kernel<HD, FUSED>, dim3(grid), dim3(kWarps * 32), smem, st, kmap, vmap, a);
     LG_LAUNCH_CHECK();
     return 0;
 }
@@ -414,6 +480,8 @@ int attn_tma_make_map(void* map_out, const void* cache_base, long long total_row
                             kKC, 64);
 }
 
+bool attn_tma_enabled() { return lg_env_flag("LG_ATTN_TMA", 1) != 0; }
+
 bool attn_tma_supported(const AttnArgs& a) {
     return a.dtype == LG_DTYPE_BF16 && a.Tq == 1 && (a.hd == 64 || a.hd == 128) && a.kmap && a.vmap && a.R <= 65535;
 }
@@ -423,13 +491,19 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     t.q = (const bf16*)a.q; t.out = (bf16*)a.out; t.R = a.R; t.H = a.H; t.maxS = a.maxS;
     t.pos_dev = a.pos.dev; t.pos_value = a.pos.value; t.row_base = a.cache_row_base;
     t.emb_mask = a.emb_mask; t.B = a.B; t.Tc = a.Tc; t.scale = a.scale;
+    t.partial = a.qkv_partial; t.ksplit = a.qkv_ksplit; t.freqs = a.freqs;
+    t.kcache = (bf16*)const_cast<void*>(a.kcache); t.vcache = (bf16*)const_cast<void*>(a.vcache);
     const CUtensorMap& km = *reinterpret_cast<const CUtensorMap*>(a.kmap);
     const CUtensorMap& vm = *reinterpret_cast<const CUtensorMap*>(a.vmap);
+    if (a.qkv_partial) {     // fused QKV epilogue
+        if (a.hd == 64) return launch_t<64, true>(km, vm, t, st);
+        return launch_t<128, true>(km, vm, t, st);
+    }
     // v2 (persistent warp-per-item, LG_ATTN_V2=1) measured SLOWER than the CTA-per-item kernel on B200 (25.7 vs
     // 19.1 us at R=128, c=128: with one warp per scheduler the ldmatrix->mma->softmax chain is latency-bound), so it
     // stays opt-in; profiles/ keeps both ncu captures.
     const bool v2 = lg_env_flag("LG_ATTN_V2", 0) && a.R * a.H >= 4 * 148 && a.hd == 64;
     if (v2) return launch_v2<64>(km, vm, t, st);
-    if (a.hd == 64) return launch_t<64>(km, vm, t, st);
-    return launch_t<128>(km, vm, t, st);
+    if (a.hd == 64) return launch_t<64, false>(km, vm, t, st);
+    return launch_t<128, false>(km, vm, t, st);
 }

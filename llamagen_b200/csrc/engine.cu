@@ -229,7 +229,6 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         QkvEpiArgs qa;
         qa.partial = ws.partial; qa.ksplit = ks; qa.M = M; qa.Tq = Tq; qa.D = D; qa.H = H; qa.hd = hd;
         qa.pos = pos; qa.freqs = freqs; qa.q = ws.q; qa.kcache = kc; qa.vcache = vc; qa.maxS = ws.max_seq; qa.dtype = dt;
-        LG_PROF(PC_QKV_EPI, st, launch_qkv_epilogue(qa, st));
         AttnArgs aa;
         aa.q = ws.q; aa.kcache = kc; aa.vcache = vc; aa.out = ws.attn; aa.R = R; aa.Tq = Tq; aa.H = H; aa.hd = hd;
         aa.maxS = ws.max_seq; aa.pos = pos; aa.emb_mask = emb_mask; aa.B = B;
@@ -237,6 +236,14 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         if (ws.have_maps) {
             aa.kmap = ws.kmap; aa.vmap = ws.vmap;
             aa.cache_row_base = (long long)l * ws.rows * H * ws.max_seq;
+        }
+        // decode steps on the TMA path: the attention kernel is also the QKV epilogue (one dependent kernel less)
+        const bool fuse_qkv = lg_env_flag("LG_FUSE_QKV", 1) && attn_tma_enabled() && attn_tma_supported(aa) &&
+                              !(lg_env_flag("LG_ATTN_V2", 0) && R * H >= 4 * 148 && hd == 64);
+        if (fuse_qkv) {
+            aa.qkv_partial = ws.partial; aa.qkv_ksplit = ks; aa.freqs = freqs;
+        } else {
+            LG_PROF(PC_QKV_EPI, st, launch_qkv_epilogue(qa, st));
         }
         LG_PROF(PC_ATTENTION, st, launch_attention(aa, st));
         LG_PROF(PC_GEMM_WO, st, gemm(ws.attn, M, D, D, ly.wo, nullptr, 0, &ks, nullptr, st, &nx_w13));

@@ -102,11 +102,14 @@ struct AttnArgs {
     // TMA path (attn_tma.cu): tensor maps over the whole K / V cache regions + this layer's first row
     const void* kmap = nullptr; const void* vmap = nullptr;
     long long cache_row_base = 0;
+    // fused QKV epilogue (TMA path, Tq == 1): the attention kernel reduces the QKV GEMM's split-K slabs itself
+    const float* qkv_partial = nullptr; int qkv_ksplit = 0; const float* freqs = nullptr;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 // attn_tma.cu — TMA + tensor-core decode attention for bf16 caches
 int attn_tma_make_map(void* map_out /*CUtensorMap, 128 B*/, const void* cache_base, long long total_rows, int hd);
 bool attn_tma_supported(const AttnArgs& a);
+bool attn_tma_enabled();
 int launch_attention_tma(const AttnArgs& a, cudaStream_t st);
 // conv_tc.cu — tcgen05 implicit-GEMM convolution over bf16 NHWC activations (TMA 4-D boxes, TMEM accumulator)
 bool conv_tc_supported(int Hin, int Win, int Cin, int Cout, int ksize, int up, bool nchw_out);

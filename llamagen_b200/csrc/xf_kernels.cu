@@ -418,7 +418,8 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t st) {
 }
 
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
-    if (attn_tma_supported(a) && lg_env_flag("LG_ATTN_TMA", 1)) return launch_attention_tma(a, st);
+    if (attn_tma_supported(a) && attn_tma_enabled()) return launch_attention_tma(a, st);
+    LG_REQUIRE(a.qkv_partial == nullptr, "attention: fused QKV epilogue requested on a path that does not support it");
     LG_REQUIRE((long long)a.R * a.Tq <= 65535, "attention: too many query rows (%d x %d)", a.R, a.Tq);
     if (a.dtype == LG_DTYPE_BF16) {
         if (a.hd == 64) return launch_attention_t<bf16, 64, 8, 8>(a, st);

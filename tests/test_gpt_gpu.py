@@ -173,15 +173,17 @@ def test_attention_kernels_agree_large_batch_t2i(monkeypatch):
         em[b, -int(lens[b]):] = 1
     cond = (torch.randn(B, 120, 64) * em[:, :, None]).bfloat16()
     outs = {}
-    for tag, env in (("v2", {"LG_ATTN_TMA": "1", "LG_ATTN_V2": "1"}), ("v1", {"LG_ATTN_TMA": "1", "LG_ATTN_V2": "0"}),
-                     ("cuda_core", {"LG_ATTN_TMA": "0", "LG_ATTN_V2": "0"})):
+    for tag, env in (("v2", {"LG_ATTN_TMA": "1", "LG_ATTN_V2": "1", "LG_FUSE_QKV": "1"}),
+                     ("v1", {"LG_ATTN_TMA": "1", "LG_ATTN_V2": "0", "LG_FUSE_QKV": "1"}),          # default: fused QKV epilogue
+                     ("v1_unfused", {"LG_ATTN_TMA": "1", "LG_ATTN_V2": "0", "LG_FUSE_QKV": "0"}),
+                     ("cuda_core", {"LG_ATTN_TMA": "0", "LG_ATTN_V2": "0", "LG_FUSE_QKV": "1"})):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         m = build_gpt(g["cfg"], g["state_dict"], torch.bfloat16)
         teacher = torch.randint(0, 512, (B, S), generator=torch.Generator().manual_seed(1), dtype=torch.int32)
         _, logits = _gen(m, cond, S, em, cfg_scale=4.0, teacher=teacher)
         outs[tag] = logits
-    for tag in ("v2", "v1"):
+    for tag in ("v2", "v1", "v1_unfused"):
         err = (outs[tag] - outs["cuda_core"]).abs().max().item()
         assert err <= BF16_TOL, (tag, err)
 
