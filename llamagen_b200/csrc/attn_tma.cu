@@ -62,7 +62,9 @@ struct AttnTmaArgs {
 // QKV GEMM; one dependent kernel per layer disappears.
 template <int HD, bool FUSED>
 __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
-                                                               const __grid_constant__ CUtensorMap vmap, AttnTmaArgs a) {
+                                                               const __grid_constant__ CUtensorMap vmap,
+                                                               const __grid_constant__ CUtensorMap kmap16,
+                                                               const __grid_constant__ CUtensorMap vmap16, AttnTmaArgs a) {
     constexpr int NSUB = HD / 64;                 // 128-byte-wide sub-tiles per row
     constexpr int SUB_BYTES = kKC * 128;          // one [kKC keys][64 dims] bf16 sub-tile
     constexpr int TILE_BYTES = NSUB * SUB_BYTES;  // K (or V) of one stage
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
     if (threadIdx.x == 0) {
         prefetch_map(&kmap);
         prefetch_map(&vmap);
+        prefetch_map(&kmap16);
+        prefetch_map(&vmap16);
         for (int s = 0; s < kStagesA; ++s) mbar_init(&full_bar[s], 1);
         fence_barrier_init();
     }
@@ -95,11 +99,27 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
         const int s = ci % kStagesA;
         uint8_t* kt = tiles + s * 2 * TILE_BYTES;
         uint8_t* vt = kt + TILE_BYTES;
-        mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+        const int row = (int)(row0 + (long long)ci * kKC);
+        const int valid = nkeys - ci * kKC;            // keys of this chunk that exist
+        if (valid >= kKC) {
+            mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
 #pragma unroll
-        for (int sub = 0; sub < NSUB; ++sub) {
-            load_2d(kt + sub * SUB_BYTES, &kmap, &full_bar[s], sub * 64, (int)(row0 + (long long)ci * kKC));
-            load_2d(vt + sub * SUB_BYTES, &vmap, &full_bar[s], sub * 64, (int)(row0 + (long long)ci * kKC));
+            for (int sub = 0; sub < NSUB; ++sub) {
+                load_2d(kt + sub * SUB_BYTES, &kmap, &full_bar[s], sub * 64, row);
+                load_2d(vt + sub * SUB_BYTES, &vmap, &full_bar[s], sub * 64, row);
+            }
+        } else {
+            // tail chunk: 16-row boxes (one per warp's key group) so at most 15 rows beyond the context are read;
+            // groups that are not loaded are never touched by the MMA loop (it skips j0 >= nkeys).
+            const int n16 = (valid + 15) / 16;
+            mbar_expect_tx(&full_bar[s], (uint32_t)(n16 * 2 * NSUB * 16 * 128));
+            for (int i = 0; i < n16; ++i) {
+#pragma unroll
+                for (int sub = 0; sub < NSUB; ++sub) {
+                    load_2d(kt + sub * SUB_BYTES + i * 2048, &kmap16, &full_bar[s], sub * 64, row + 16 * i);
+                    load_2d(vt + sub * SUB_BYTES + i * 2048, &vmap16, &full_bar[s], sub * 64, row + 16 * i);
+                }
+            }
         }
     };
     const int npro = min(kStagesA, nchunks);
@@ -457,7 +477,8 @@ int launch_v2(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnTmaArg
 }
 
 template <int HD, bool FUSED>
-int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnTmaArgs& a, cudaStream_t st) {
+int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const CUtensorMap& kmap16, const CUtensorMap& vmap16,
+             const AttnTmaArgs& a, cudaStream_t st) {
     constexpr int TILE_BYTES = (HD / 64) * kKC * 128;
     const size_t smem = 1024 + (size_t)kStagesA * 2 * TILE_BYTES + kStagesA * sizeof(uint64_t) +
                         (kWarps + 1) * (HD + 2) * sizeof(float) + 3 * HD * sizeof(bf16) + 16;
@@ -467,7 +488,7 @@ int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnTmaArgs
         attr = true;
     }
     dim3 grid(a.H, a.R);
-    (void)lg_launch(attn_tma_kernel<HD, FUSED>, dim3(grid), dim3(kWarps * 32), smem, st, kmap, vmap, a);
+    (void)lg_launch(attn_tma_kernel<HD, FUSED>, dim3(grid), dim3(kWarps * 32), smem, st, kmap, vmap, kmap16, vmap16, a);
     LG_LAUNCH_CHECK();
     return 0;
 }
@@ -475,15 +496,15 @@ int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnTmaArgs
 }  // namespace
 
 // KV-cache tensor maps: the whole K (or V) region of the workspace as one [rows, hd] bf16 matrix
-int attn_tma_make_map(void* map_out, const void* cache_base, long long total_rows, int hd) {
+int attn_tma_make_map(void* map_out, const void* cache_base, long long total_rows, int hd, int tail16) {
     return tma::make_map_2d(reinterpret_cast<CUtensorMap*>(map_out), cache_base, (uint64_t)total_rows, (uint64_t)hd, (uint64_t)hd,
-                            kKC, 64);
+                            tail16 ? 16 : kKC, 64);
 }
 
 bool attn_tma_enabled() { return lg_env_flag("LG_ATTN_TMA", 1) != 0; }
 
 bool attn_tma_supported(const AttnArgs& a) {
-    return a.dtype == LG_DTYPE_BF16 && a.Tq == 1 && (a.hd == 64 || a.hd == 128) && a.kmap && a.vmap && a.R <= 65535;
+    return a.dtype == LG_DTYPE_BF16 && a.Tq == 1 && (a.hd == 64 || a.hd == 128) && a.kmap && a.vmap && a.kmap16 && a.vmap16 && a.R <= 65535;
 }
 
 int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
@@ -495,15 +516,17 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     t.kcache = (bf16*)const_cast<void*>(a.kcache); t.vcache = (bf16*)const_cast<void*>(a.vcache);
     const CUtensorMap& km = *reinterpret_cast<const CUtensorMap*>(a.kmap);
     const CUtensorMap& vm = *reinterpret_cast<const CUtensorMap*>(a.vmap);
+    const CUtensorMap& km16 = *reinterpret_cast<const CUtensorMap*>(a.kmap16);
+    const CUtensorMap& vm16 = *reinterpret_cast<const CUtensorMap*>(a.vmap16);
     if (a.qkv_partial) {     // fused QKV epilogue
-        if (a.hd == 64) return launch_t<64, true>(km, vm, t, st);
-        return launch_t<128, true>(km, vm, t, st);
+        if (a.hd == 64) return launch_t<64, true>(km, vm, km16, vm16, t, st);
+        return launch_t<128, true>(km, vm, km16, vm16, t, st);
     }
     // v2 (persistent warp-per-item, LG_ATTN_V2=1) measured SLOWER than the CTA-per-item kernel on B200 (25.7 vs
     // 19.1 us at R=128, c=128: with one warp per scheduler the ldmatrix->mma->softmax chain is latency-bound), so it
     // stays opt-in; profiles/ keeps both ncu captures.
     const bool v2 = lg_env_flag("LG_ATTN_V2", 0) && a.R * a.H >= 4 * 148 && a.hd == 64;
     if (v2) return launch_v2<64>(km, vm, t, st);
-    if (a.hd == 64) return launch_t<64, false>(km, vm, t, st);
-    return launch_t<128, false>(km, vm, t, st);
+    if (a.hd == 64) return launch_t<64, false>(km, vm, km16, vm16, t, st);
+    return launch_t<128, false>(km, vm, km16, vm16, t, st);
 }

@@ -115,6 +115,8 @@ struct Workspace {
     size_t partial_floats = 0;
     alignas(64) unsigned char kmap[128];   // CUtensorMap over the K / V cache regions (bf16 only)
     alignas(64) unsigned char vmap[128];
+    alignas(64) unsigned char kmap16[128];  // same regions, 16-row boxes (tail chunk of the decode attention)
+    alignas(64) unsigned char vmap16[128];
     bool have_maps = false;
 };
 
@@ -234,7 +236,7 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         aa.maxS = ws.max_seq; aa.pos = pos; aa.emb_mask = emb_mask; aa.B = B;
         aa.Tc = cfg.cls_token_num; aa.scale = 1.0f / sqrtf((float)hd); aa.dtype = dt;
         if (ws.have_maps) {
-            aa.kmap = ws.kmap; aa.vmap = ws.vmap;
+            aa.kmap = ws.kmap; aa.vmap = ws.vmap; aa.kmap16 = ws.kmap16; aa.vmap16 = ws.vmap16;
             aa.cache_row_base = (long long)l * ws.rows * H * ws.max_seq;
         }
         // decode steps on the TMA path: the attention kernel is also the QKV epilogue (one dependent kernel less)
@@ -408,6 +410,8 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
         if (total_rows < (1ll << 31)) {
             LG_TRY(attn_tma_make_map(tmp.kmap, tmp.kcache, total_rows, e->hd));
             LG_TRY(attn_tma_make_map(tmp.vmap, tmp.vcache, total_rows, e->hd));
+            LG_TRY(attn_tma_make_map(tmp.kmap16, tmp.kcache, total_rows, e->hd, 1));
+            LG_TRY(attn_tma_make_map(tmp.vmap16, tmp.vcache, total_rows, e->hd, 1));
             tmp.have_maps = true;
         }
     }
@@ -448,6 +452,8 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
                 const long long total_rows = (long long)c.n_layer * hr * c.n_head * max_seq;
                 LG_TRY(attn_tma_make_map(w.kmap, w.kcache, total_rows, e->hd));
                 LG_TRY(attn_tma_make_map(w.vmap, w.vcache, total_rows, e->hd));
+                LG_TRY(attn_tma_make_map(w.kmap16, w.kcache, total_rows, e->hd, 1));
+                LG_TRY(attn_tma_make_map(w.vmap16, w.vcache, total_rows, e->hd, 1));
                 w.have_maps = true;
                 e->sub[g] = w;
             }

@@ -100,14 +100,15 @@ struct AttnArgs {
     float scale;
     int dtype;
     // TMA path (attn_tma.cu): tensor maps over the whole K / V cache regions + this layer's first row
-    const void* kmap = nullptr; const void* vmap = nullptr;
+    const void* kmap = nullptr; const void* vmap = nullptr;        // kKC-row boxes
+    const void* kmap16 = nullptr; const void* vmap16 = nullptr;    // 16-row boxes for the tail chunk
     long long cache_row_base = 0;
     // fused QKV epilogue (TMA path, Tq == 1): the attention kernel reduces the QKV GEMM's split-K slabs itself
     const float* qkv_partial = nullptr; int qkv_ksplit = 0; const float* freqs = nullptr;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 // attn_tma.cu — TMA + tensor-core decode attention for bf16 caches
-int attn_tma_make_map(void* map_out /*CUtensorMap, 128 B*/, const void* cache_base, long long total_rows, int hd);
+int attn_tma_make_map(void* map_out /*CUtensorMap, 128 B*/, const void* cache_base, long long total_rows, int hd, int tail16 = 0);
 bool attn_tma_supported(const AttnArgs& a);
 bool attn_tma_enabled();
 int launch_attention_tma(const AttnArgs& a, cudaStream_t st);
