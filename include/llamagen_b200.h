@@ -134,6 +134,17 @@ int  lg_vq_decode(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws,
                   float* out_nchw, void* stream);
 /* VectorQuantizer.forward index path (vq_model.py:215-233): z dev f32 NCHW [B, e_dim, g, g] -> idx int64 [B*g*g]. */
 int  lg_vq_argmin(lg_vq* v, const float* z_nchw, int B, int grid, int64_t* out_idx, void* stream);
+/* VQModel.encode (vq_model.py:41-45): Encoder.forward :100-124 (Downsample :389-397) -> quant_conv -> VectorQuantizer.forward
+ * :215-255 in eval mode. x dev f32 NCHW [B,3,H,W] (square, H a multiple of 2^(n_mult-1)) -> out_idx dev int64 [B*g*g];
+ * optional out_quant dev f32 NCHW [B,e_dim,g,g] (the straight-through tensor z + (e[idx] - z)) and out_z (pre-quantisation
+ * quant_conv output), either may be NULL. Needs the encoder.* and quant_conv.* tensors bound before lg_vq_finalize; the
+ * encoder uses ch_mult of the cfg (the reference's encoder_ch_mult == decoder_ch_mult in both registry entries,
+ * vq_model.py:418-422). Workspace: lg_vq_workspace_bytes(B, H / 2^(n_mult-1)). */
+int  lg_vq_encode(lg_vq* v, const float* x_nchw, int B, int H, int W, void* dev_ws, size_t ws_bytes, int64_t* out_idx,
+                  float* out_quant_nchw, float* out_z_nchw, void* stream);
+/* Pixel finishing of the samplers (sample_c2i_ddp.py:141-143): optional F.interpolate(mode='bicubic') to out_h x out_w,
+ * then clamp(127.5*x + 128, 0, 255) -> uint8, NCHW f32 in -> NHWC u8 out, one pass. */
+int  lg_pixels_to_u8(const float* in_nchw, int B, int C, int H, int W, int out_h, int out_w, uint8_t* out_nhwc, void* stream);
 
 /* ---- per-kernel-class device timing for bench.py's roofline leg --------------------------------------
  * While enabled, launches are bracketed by CUDA events on the launching stream (CUDA-graph replay is bypassed).

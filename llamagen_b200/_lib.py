@@ -64,6 +64,9 @@ SIGNATURES = {
     "lg_vq_workspace_bytes": (c_int, [c_void_p, c_int, c_int, POINTER(c_size_t)]),
     "lg_vq_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "lg_vq_argmin": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "lg_vq_encode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
+                             c_void_p]),
+    "lg_pixels_to_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "lg_set_pdl": (c_int, [c_int]),
     "lg_profile_enable": (c_int, [c_int]),
     "lg_profile_reset": (c_int, []),

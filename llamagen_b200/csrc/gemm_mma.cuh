@@ -57,6 +57,7 @@ struct ConvA {               // NHWC input [B, Hin, Win, Cin]; output pixel grid
     int Hin, Win, Cin, Hout, Wout;
     int ksize;               // 1 or 3 (pad = ksize/2, stride 1)
     int up;                  // 1: input is nearest-upsampled x2 on the fly (Hout = 2*Hin)
+                             // 2: Downsample (vq_model.py:389-397): zero pad right/bottom by one, 3x3 stride 2, Hout = Hin/2
     int M;                   // B*Hout*Wout
     struct Row { int b, y, x; };
     __device__ __forceinline__ Row row(int m, int) const {
@@ -76,6 +77,13 @@ struct ConvA {               // NHWC input [B, Hin, Win, Cin]; output pixel grid
         if (r.b < 0) return nullptr;
         const int tap = k / Cin, c = k - tap * Cin;
         int yy = r.y, xx = r.x;
+        if (up == 2) {
+            const int ty = tap / 3;
+            yy = 2 * yy + ty;
+            xx = 2 * xx + tap - ty * 3;
+            if (yy >= Hin || xx >= Win) return nullptr;
+            return in + (((long long)r.b * Hin + yy) * Win + xx) * Cin + c;
+        }
         if (ksize == 3) {
             const int ty = tap / 3;
             yy += ty - 1;

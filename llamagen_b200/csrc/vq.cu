@@ -277,13 +277,138 @@ __global__ void __launch_bounds__(128) argmin_kernel(const float* __restrict__ z
     if (i < nz) out[i] = besti;
 }
 
+
+// ------------------------------------------------------------------------------------------------ encoder front / pixel back
+// Encoder.conv_in (vq_model.py:70,101): 3x3 pad 1, 3 -> ch, evaluated in fp32 straight from the fp32 NCHW image
+// (K = 27 is far too thin for a tensor-core tile); writes the bf16 NHWC activation the rest of the encoder consumes.
+// One thread = one pixel x 8 output channels; weights are staged transposed ([tap][ch]) in shared memory.
+__global__ void __launch_bounds__(256) conv_in_rgb_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, bf16* __restrict__ out, int B, int H,
+                                                          int W, int ch) {
+    extern __shared__ float ws[];   // [27][ch] then bias [ch]
+    for (int i = threadIdx.x; i < 27 * ch; i += blockDim.x) {
+        const int c = i / 27, t = i - c * 27;               // source layout [ch][cin=3][ky][kx] -> t = cin*9 + ky*3 + kx
+        ws[t * ch + c] = w[i];
+    }
+    for (int i = threadIdx.x; i < ch; i += blockDim.x) ws[27 * ch + i] = bias[i];
+    __syncthreads();
+    const int oct = ch / 8;
+    const long long total = (long long)B * H * W * oct;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int o = (int)(gid % oct);
+    const long long pix = gid / oct;
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = ws[27 * ch + o * 8 + j];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        const float* plane = x + ((long long)b * 3 + ci) * H * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int y2 = yy + ky - 1;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int x2 = xx + kx - 1;
+                const float v = ((unsigned)y2 < (unsigned)H && (unsigned)x2 < (unsigned)W) ? plane[(long long)y2 * W + x2] : 0.f;
+                const float* wr = ws + (ci * 9 + ky * 3 + kx) * ch + o * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+            }
+        }
+    }
+    uint4 pk;
+    __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + pix * ch + o * 8) = pk;
+}
+
+// VectorQuantizer.forward's returned tensor (vq_model.py:233,252-255): z_q = z + (e[idx] - z) with z L2-normalised
+// when codebook_l2_norm; NCHW in, NCHW out. One thread per latent position.
+__global__ void quant_out_kernel(const float* __restrict__ z, const int64_t* __restrict__ idx, const float* __restrict__ cb,
+                                 int B, int hw, int ed, int l2norm, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * hw) return;
+    const int b = i / hw, p = i - b * hw;
+    const float* zp = z + (long long)b * ed * hw + p;
+    float inv = 1.f;
+    if (l2norm) {
+        float ss = 0.f;
+        for (int c = 0; c < ed; ++c) ss = __fadd_rn(ss, __fmul_rn(zp[(long long)c * hw], zp[(long long)c * hw]));
+        inv = fmaxf(sqrtf(ss), 1e-12f);                     // F.normalize: x / max(||x||, eps)
+    }
+    const float* e = cb + idx[i] * ed;
+    for (int c = 0; c < ed; ++c) {
+        const float zn = l2norm ? __fdiv_rn(zp[(long long)c * hw], inv) : zp[(long long)c * hw];
+        out[((long long)b * ed + c) * hw + p] = __fadd_rn(zn, __fsub_rn(e[c], zn));
+    }
+}
+
+// Pixel finishing of the DDP sampler (sample_c2i_ddp.py:141-143) in one pass: optional bicubic resize
+// (F.interpolate(mode='bicubic'), align_corners=False, A = -0.75, border-clamped taps, no antialias), then
+// clamp(127.5 x + 128, 0, 255) -> uint8 (truncation) in NHWC. fp32 NCHW in. One thread per output pixel, all C channels.
+__device__ __forceinline__ void cubic_coeffs(float t, float* c) {
+    const float A = -0.75f;
+    const float x0 = t + 1.f, x3 = 2.f - t, x2 = 1.f - t;
+    c[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+    c[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+    c[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+    c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+__global__ void __launch_bounds__(256) pixels_to_u8_kernel(const float* __restrict__ in, int B, int C, int H, int W, int OH, int OW,
+                                                           uint8_t* __restrict__ out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * OH * OW) return;
+    const int ox = (int)(gid % OW);
+    const int oy = (int)((gid / OW) % OH);
+    const int b = (int)(gid / ((long long)OW * OH));
+    const bool resize = OH != H || OW != W;
+    float cy[4], cx[4];
+    int iy = oy, ix = ox;
+    if (resize) {
+        const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+        const float fy = sy * ((float)oy + 0.5f) - 0.5f, fx = sx * ((float)ox + 0.5f) - 0.5f;
+        iy = (int)floorf(fy); ix = (int)floorf(fx);
+        cubic_coeffs(fy - (float)iy, cy);
+        cubic_coeffs(fx - (float)ix, cx);
+    }
+    for (int c = 0; c < C; ++c) {
+        const float* plane = in + ((long long)b * C + c) * H * W;
+        float v;
+        if (!resize) {
+            v = plane[(long long)oy * W + ox];
+        } else {
+            v = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int yy = min(max(iy - 1 + i, 0), H - 1);
+                float r = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = min(max(ix - 1 + j, 0), W - 1);
+                    r += plane[(long long)yy * W + xx] * cx[j];
+                }
+                v += r * cy[i];
+            }
+        }
+        v = __fadd_rn(__fmul_rn(127.5f, v), 128.0f);
+        v = fminf(fmaxf(v, 0.f), 255.f);
+        out[gid * C + c] = (uint8_t)v;                       // truncation toward zero, like Tensor.to(torch.uint8)
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ model structs
 struct HostTensor { const float* p = nullptr; int64_t shape[4] = {0, 0, 0, 0}; int ndim = 0; };
 struct ConvW { bf16* w = nullptr; bf16* w_phase = nullptr; const float* bias = nullptr; int cout = 0, cin = 0, k = 0; };
 struct NormW { const float* gamma = nullptr; const float* beta = nullptr; int c = 0; };
 struct ResW { NormW n1, n2; ConvW c1, c2, nin; bool has_nin = false; int cin = 0, cout = 0; };
 struct AttnW { NormW norm; ConvW qk, v, proj; float* qk_bias = nullptr; int c = 0; };
-struct LevelW { std::vector<ResW> res; std::vector<AttnW> attn; bool up = false; ConvW upconv; };
+struct LevelW { std::vector<ResW> res; std::vector<AttnW> attn; bool up = false; ConvW upconv; };   // upconv: up- or downsample conv
 
 }  // namespace
 
@@ -302,6 +427,15 @@ struct lg_vq {
     float* codebook_sq = nullptr;
     const float* pq_w = nullptr;
     const float* pq_b = nullptr;
+    // encoder (optional: built when encoder.* and quant_conv.* are bound)
+    bool has_encoder = false;
+    const float* enc_in_w = nullptr;   // fp32 [ch,3,3,3], applied in fp32 by conv_in_rgb_kernel
+    const float* enc_in_b = nullptr;
+    std::vector<LevelW> enc_levels;
+    ResW enc_mid0, enc_mid2;
+    AttnW enc_mid1;
+    NormW enc_norm_out;
+    ConvW enc_conv_out, quant_conv;
 
     ~lg_vq() { for (void* p : owned) cudaFree(p); }
 };
@@ -388,7 +522,7 @@ int make_attn(lg_vq* v, const std::string& p, int c, AttnW* a, cudaStream_t st) 
 // workspace carve (per chunk of Bc images)
 struct VqWs {
     bf16 *X, *T, *U, *VT, *P;
-    float *S, *gn;
+    float *S, *gn, *Z;
     size_t bytes;
     int attn_bc;   // images per attention chunk
 };
@@ -420,6 +554,7 @@ VqWs carve_vq(const lg_vq* v, char* base, int Bc, int g) {
     w.S = (float*)take((size_t)abc * N * N * 4);
     w.P = (bf16*)take((size_t)abc * N * N * 2);
     w.gn = (float*)take((size_t)Bc * 64 * 32 * 2 * 4);
+    w.Z = (float*)take((size_t)Bc * N * c.codebook_embed_dim * 4);   // encoder output z (fp32 NCHW) ahead of the argmin
     w.bytes = off;
     w.attn_bc = abc;
     return w;
@@ -434,15 +569,16 @@ int chunk_images(const lg_vq* v, int B, int g) {
 }
 
 // ---- layer launchers --------------------------------------------------------------------------------
+// up: 0 = same resolution, 1 = nearest-2x upsample folded in, 2 = Downsample (pad right/bottom, stride 2)
 int run_conv(const ConvW& cw, const bf16* in, int B, int Hin, int Win, int up, const bf16* residual, bf16* out_bf,
              float* out_nchw, cudaStream_t st) {
-    if (lg_env_flag("LG_CONV_TC", 1) && conv_tc_supported(Hin, Win, cw.cin, cw.cout, cw.k, up, out_nchw != nullptr) &&
+    if (up != 2 && lg_env_flag("LG_CONV_TC", 1) && conv_tc_supported(Hin, Win, cw.cin, cw.cout, cw.k, up, out_nchw != nullptr) &&
         (!up || cw.w_phase)) {
         LG_PROF(PC_VQ_CONV, st, launch_conv_tc(in, B, Hin, Win, cw.cin, up ? cw.w_phase : cw.w, cw.bias, cw.cout, cw.k, up, residual,
                                                out_bf, out_nchw, st));
         return 0;
     }
-    const int Hout = up ? 2 * Hin : Hin, Wout = up ? 2 * Win : Win;
+    const int Hout = up == 1 ? 2 * Hin : (up == 2 ? Hin / 2 : Hin), Wout = up == 1 ? 2 * Win : (up == 2 ? Win / 2 : Win);
     const int M = B * Hout * Wout, K = cw.k * cw.k * cw.cin;
     mma::ConvA al{in, Hin, Win, cw.cin, Hout, Wout, cw.k, up, M};
     mma::BRows bw{cw.w, cw.w, cw.cout, K, 0, cw.cout};
@@ -610,6 +746,40 @@ int lg_vq_finalize(lg_vq* v, void* stream) {
     }
     LG_TRY(make_norm(v, "decoder.norm_out", block_in, &v->norm_out));
     LG_TRY(make_conv(v, "decoder.conv_out", 3, block_in, 3, &v->conv_out, st));
+    // ---- encoder (vq_model.py:64-97) + quant_conv (:35): only when the caller bound those tensors
+    v->enc_levels.clear();
+    v->has_encoder = v->t.count("encoder.conv_in.weight") && v->t.count("quant_conv.weight");
+    if (v->has_encoder) {
+        LG_REQUIRE(c.ch % 8 == 0, "encoder: ch=%d must be a multiple of 8", c.ch);
+        LG_TRY(get(v, "encoder.conv_in.weight", {c.ch, 3, 3, 3}, &v->enc_in_w));
+        LG_TRY(get(v, "encoder.conv_in.bias", {c.ch}, &v->enc_in_b));
+        int bin = c.ch;
+        for (int i_level = 0; i_level < n; ++i_level) {
+            const int bout = c.ch * c.ch_mult[i_level];
+            const std::string p = "encoder.conv_blocks." + std::to_string(i_level);
+            LevelW lv;
+            for (int j = 0; j < nrb; ++j) {
+                ResW r;
+                LG_TRY(make_res(v, p + ".res." + std::to_string(j), bin, bout, &r, st));
+                lv.res.push_back(r);
+                bin = bout;
+                if (i_level == n - 1) {
+                    AttnW a;
+                    LG_TRY(make_attn(v, p + ".attn." + std::to_string(j), bin, &a, st));
+                    lv.attn.push_back(a);
+                }
+            }
+            lv.up = i_level != n - 1;   // here: has a Downsample conv
+            if (lv.up) LG_TRY(make_conv(v, p + ".downsample.conv", bin, bin, 3, &lv.upconv, st));
+            v->enc_levels.push_back(lv);
+        }
+        LG_TRY(make_res(v, "encoder.mid.0", bin, bin, &v->enc_mid0, st));
+        LG_TRY(make_attn(v, "encoder.mid.1", bin, &v->enc_mid1, st));
+        LG_TRY(make_res(v, "encoder.mid.2", bin, bin, &v->enc_mid2, st));
+        LG_TRY(make_norm(v, "encoder.norm_out", bin, &v->enc_norm_out));
+        LG_TRY(make_conv(v, "encoder.conv_out", c.z_channels, bin, 3, &v->enc_conv_out, st));
+        LG_TRY(make_conv(v, "quant_conv", c.codebook_embed_dim, c.z_channels, 1, &v->quant_conv, st));
+    }
     LG_CUDA_OK(cudaStreamSynchronize(st));
     v->finalized = true;
     return 0;
@@ -679,6 +849,70 @@ int lg_vq_argmin(lg_vq* v, const float* z_nchw, int B, int grid, int64_t* out_id
     else if (ed == 16) LG_ARGMIN(16);
     else LG_ARGMIN(32);
 #undef LG_ARGMIN
+    LG_LAUNCH_CHECK();
+    return 0;
+}
+
+int lg_vq_encode(lg_vq* v, const float* x_nchw, int B, int H, int W, void* dev_ws, size_t ws_bytes, int64_t* out_idx,
+                 float* out_quant_nchw, float* out_z_nchw, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LG_REQUIRE(v && v->finalized, "vq engine not finalized");
+    LG_REQUIRE(v->has_encoder, "lg_vq_encode: encoder.* / quant_conv.* weights were not bound");
+    LG_REQUIRE(x_nchw && dev_ws && out_idx && B > 0, "lg_vq_encode: bad argument");
+    LG_REQUIRE(((uintptr_t)dev_ws & 255) == 0, "workspace must be 256-byte aligned");
+    const lg_vq_cfg& c = v->cfg;
+    const int down = 1 << (c.n_mult - 1);
+    LG_REQUIRE(H == W && H > 0 && H % down == 0, "lg_vq_encode: image %dx%d must be square and a multiple of %d", H, W, down);
+    const int grid = H / down, N = grid * grid, ed = c.codebook_embed_dim;
+    const int Bc = chunk_images(v, B, grid);
+    VqWs w = carve_vq(v, (char*)dev_ws, Bc, grid);
+    LG_REQUIRE(ws_bytes >= w.bytes, "vq workspace too small: %zu < %zu", ws_bytes, w.bytes);
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int bc = std::min(Bc, B - b0);
+        int h = H, wd = W;
+        {
+            const long long threads = (long long)bc * h * wd * (c.ch / 8);
+            const size_t smem = (size_t)28 * c.ch * sizeof(float);
+            prof_begin(PC_VQ_CONV, st);
+            conv_in_rgb_kernel<<<(unsigned)cdiv(threads, 256), 256, smem, st>>>(x_nchw + (size_t)b0 * 3 * H * W, v->enc_in_w,
+                                                                                v->enc_in_b, w.X, bc, h, wd, c.ch);
+            prof_end(st);
+            LG_LAUNCH_CHECK();
+        }
+        for (size_t li = 0; li < v->enc_levels.size(); ++li) {
+            const LevelW& lv = v->enc_levels[li];
+            for (size_t j = 0; j < lv.res.size(); ++j) {
+                LG_TRY(run_res(lv.res[j], w, bc, h, wd, st));
+                if (!lv.attn.empty()) LG_TRY(run_attn(lv.attn[j], w, bc, h, wd, st));
+            }
+            if (lv.up) {
+                LG_TRY(run_conv(lv.upconv, w.X, bc, h, wd, 2, nullptr, w.T, nullptr, st));
+                std::swap(w.X, w.T);
+                h /= 2; wd /= 2;
+            }
+        }
+        LG_TRY(run_res(v->enc_mid0, w, bc, h, wd, st));
+        LG_TRY(run_attn(v->enc_mid1, w, bc, h, wd, st));
+        LG_TRY(run_res(v->enc_mid2, w, bc, h, wd, st));
+        LG_TRY(run_gn(v->enc_norm_out, w.X, w.T, bc, h * wd, 1, w.gn, st));
+        LG_TRY(run_conv(v->enc_conv_out, w.T, bc, h, wd, 0, nullptr, w.U, nullptr, st));
+        float* z = out_z_nchw ? out_z_nchw + (size_t)b0 * ed * N : w.Z;
+        LG_TRY(run_conv(v->quant_conv, w.U, bc, h, wd, 0, nullptr, nullptr, z, st));
+        LG_TRY(lg_vq_argmin(v, z, bc, grid, out_idx + (size_t)b0 * N, stream));
+        if (out_quant_nchw) {
+            quant_out_kernel<<<cdiv(bc * N, 256), 256, 0, st>>>(z, out_idx + (size_t)b0 * N, v->codebook, bc, N, ed, c.l2_norm,
+                                                               out_quant_nchw + (size_t)b0 * ed * N);
+            LG_LAUNCH_CHECK();
+        }
+    }
+    return 0;
+}
+
+int lg_pixels_to_u8(const float* in_nchw, int B, int C, int H, int W, int out_h, int out_w, uint8_t* out_nhwc, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LG_REQUIRE(in_nchw && out_nhwc && B > 0 && C > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "lg_pixels_to_u8: bad argument");
+    const long long n = (long long)B * out_h * out_w;
+    pixels_to_u8_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(in_nchw, B, C, H, W, out_h, out_w, out_nhwc);
     LG_LAUNCH_CHECK();
     return 0;
 }

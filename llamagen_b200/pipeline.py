@@ -10,6 +10,7 @@ from __future__ import annotations
 import torch
 
 from .generate import generate
+from .postprocess import to_uint8_nhwc
 
 
 class SamplePipeline:
@@ -25,8 +26,9 @@ class SamplePipeline:
     def submit(self, cond, grid: int, to_uint8_host=None):
         """Enqueue generate() on the current stream and decode_code() on the decode stream. Returns the pixel tensor
         (fp32 NCHW); it is complete once `self.decode_stream` (or `wait()`) has been synchronised. When
-        `to_uint8_host` (a pinned uint8 [B,H,W,3] tensor) is given, the clamp/convert of sample_c2i_ddp.py:143 and the
-        device-to-host copy are enqueued behind the decode as well."""
+        `to_uint8_host` (a pinned uint8 [B,H',W',3] tensor) is given, the pixel finishing of sample_c2i_ddp.py:141-143
+        (bicubic resize to H' x W' when that differs from the decoder's output, clamp, uint8, NHWC — one kernel,
+        postprocess.to_uint8_nhwc) and the device-to-host copy are enqueued behind the decode as well."""
         main = torch.cuda.current_stream(self.dev)
         tokens = generate(self.gpt, cond, grid * grid, **self.kw)
         ready = torch.cuda.Event()
@@ -36,7 +38,7 @@ class SamplePipeline:
         with torch.cuda.stream(self.decode_stream):
             pixels = self.vq.decode_code(tokens, [tokens.shape[0], self.embed_dim, grid, grid])
             if to_uint8_host is not None:
-                u8 = torch.clamp(127.5 * pixels + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+                u8 = to_uint8_nhwc(pixels, size=(to_uint8_host.shape[1], to_uint8_host.shape[2]))
                 to_uint8_host.copy_(u8, non_blocking=True)
         self._last = pixels
         return pixels

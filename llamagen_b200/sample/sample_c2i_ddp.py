@@ -1,7 +1,8 @@
 """`torchrun --nproc_per_node=N -m llamagen_b200.sample.sample_c2i_ddp` — replica data-parallel sampler with the
 flags of autoregressive/sample/sample_c2i_ddp.py:161-187: per-rank seed global_seed*world+rank (:47), per-rank
 generate() + decode_code(), PNG index i*world+rank+total (:147), rank-0 .npz (:21-35). Differences: weights are
-loaded / initialised by rank 0 and broadcast over NCCL once, instead of every rank reading the checkpoint."""
+loaded / initialised by rank 0 and broadcast over NCCL once, instead of every rank reading the checkpoint; the pixel
+finishing (:141-143) is one CUDA kernel and the PNG encoders run on host threads under the next batch's sampling."""
 import argparse
 import math
 import os
@@ -9,10 +10,10 @@ import os
 import numpy as np
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
 from .. import distributed as lgd
-from .. import generate
+from ..pipeline import SamplePipeline
+from ..postprocess import AsyncPngWriter
 from .common import add_common_args, load_gpt, load_vq
 
 
@@ -58,19 +59,34 @@ def main(args):
     total_samples = int(math.ceil(args.num_fid_samples / global_batch) * global_batch)
     iterations = total_samples // world // n
     total = 0
-    from PIL import Image
-    for _ in range(iterations):
-        c_indices = torch.randint(0, args.num_classes, (n,), device=device)
-        qzshape = [n, args.codebook_embed_dim, latent_size, latent_size]
-        index_sample = generate(gpt_model, c_indices, latent_size ** 2, cfg_scale=args.cfg_scale, cfg_interval=args.cfg_interval,
-                                temperature=args.temperature, top_k=args.top_k, top_p=args.top_p, sample_logits=True)
-        samples = vq_model.decode_code(index_sample, qzshape)
-        if args.image_size_eval != args.image_size:
-            samples = F.interpolate(samples, size=(args.image_size_eval, args.image_size_eval), mode="bicubic")
-        samples = torch.clamp(127.5 * samples + 128.0, 0, 255).permute(0, 2, 3, 1).to("cpu", dtype=torch.uint8).numpy()
-        for i, sample in enumerate(samples):
-            Image.fromarray(sample).save(f"{sample_folder_dir}/{lgd.image_index(i, rank, world, total):06d}.png")
-        total += global_batch
+    # Steady-state loop of sample_c2i_ddp.py:128-149, reorganised: the VQ decode + pixel finishing +
+    # D2H of batch i run on a second stream under the AR sampling of batch i+1, and the PNG encoders run on host
+    # threads; file names and contents are the reference's.
+    pipe = SamplePipeline(gpt_model, vq_model, args.codebook_embed_dim, cfg_scale=args.cfg_scale, cfg_interval=args.cfg_interval,
+                          temperature=args.temperature, top_k=args.top_k, top_p=args.top_p, sample_logits=True)
+    eval_px = args.image_size_eval
+    host = [torch.empty(n, eval_px, eval_px, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def flush(job, writer):
+        done, buf, base = job
+        done.synchronize()
+        for i in range(n):
+            writer.submit(buf[i].numpy().copy(), f"{sample_folder_dir}/{lgd.image_index(i, rank, world, base):06d}.png")
+
+    with AsyncPngWriter(args.png_workers) as writer:
+        pending = None
+        for it in range(iterations):
+            c_indices = torch.randint(0, args.num_classes, (n,), device=device)
+            buf = host[it % 2]
+            pipe.submit(c_indices, latent_size, to_uint8_host=buf)
+            done = torch.cuda.Event()
+            done.record(pipe.decode_stream)
+            if pending is not None:
+                flush(pending, writer)
+            pending = (done, buf, total)
+            total += global_batch
+        if pending is not None:
+            flush(pending, writer)
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -89,6 +105,7 @@ def build_parser():
     parser.add_argument("--per-proc-batch-size", type=int, default=32)
     parser.add_argument("--num-fid-samples", type=int, default=50000)
     parser.add_argument("--global-seed", type=int, default=0)
+    parser.add_argument("--png-workers", type=int, default=8, help="host threads encoding PNGs (extra flag, not in the reference)")
     return parser
 
 

@@ -153,10 +153,14 @@ class VQModel(nn.Module):
         self._ws = None
 
     # ------------------------------------------------------------------ engine plumbing
+    def _has_encoder_path(self):
+        # the engine builds the encoder with the cfg's single ch_mult; both registry entries use equal lists (vq_model.py:418-422)
+        return list(self.config.encoder_ch_mult) == list(self.config.decoder_ch_mult)
+
     def _decode_tensors(self):
         sd = self.state_dict()
-        return {k: v for k, v in sd.items()
-                if k.startswith("decoder.") or k.startswith("post_quant_conv.") or k == "quantize.embedding.weight"}
+        keep = ("decoder.", "post_quant_conv.") + (("encoder.", "quant_conv.") if self._has_encoder_path() else ())
+        return {k: v for k, v in sd.items() if k.startswith(keep) or k == "quantize.embedding.weight"}
 
     def engine(self):
         tensors = self._decode_tensors()
@@ -211,13 +215,8 @@ class VQModel(nn.Module):
         codes = code_b.to(device=dev, dtype=torch.int32).reshape(B, g * g).contiguous()
         up = 2 ** (len(self.config.decoder_ch_mult) - 1)
         out = torch.empty(B, 3, g * up, g * up, dtype=torch.float32, device=dev)
-        nbytes = ctypes.c_size_t()
-        _lib.check(lib.lg_vq_workspace_bytes(h, B, g, ctypes.byref(nbytes)), "lg_vq_workspace_bytes")
-        if self._ws is None or self._ws.numel() < nbytes.value + 256:
-            self._ws = None
-            self._ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
-        base = (self._ws.data_ptr() + 255) // 256 * 256
-        _lib.check(lib.lg_vq_decode(h, _lib.ptr(codes), B, g, ctypes.c_void_p(base), nbytes.value, _lib.ptr(out),
+        base, nbytes = self._workspace(h, B, g, dev)
+        _lib.check(lib.lg_vq_decode(h, _lib.ptr(codes), B, g, ctypes.c_void_p(base), nbytes, _lib.ptr(out),
                                     _lib.current_stream(dev)), "lg_vq_decode")
         return out
 
@@ -234,8 +233,38 @@ class VQModel(nn.Module):
         _lib.check(_lib.load().lg_vq_argmin(h, _lib.ptr(z), B, g, _lib.ptr(out), _lib.current_stream(dev)), "lg_vq_argmin")
         return out
 
-    def encode(self, x):
-        raise NotImplementedError("the conv encoder is the next-tier row (SURVEY §8f-2); use quantize_indices for the argmin-L2 kernel")
+    def _workspace(self, h, B, g, dev):
+        nbytes = ctypes.c_size_t()
+        _lib.check(_lib.load().lg_vq_workspace_bytes(h, B, g, ctypes.byref(nbytes)), "lg_vq_workspace_bytes")
+        if self._ws is None or self._ws.numel() < nbytes.value + 256:
+            self._ws = None
+            self._ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+        return (self._ws.data_ptr() + 255) // 256 * 256, nbytes.value
+
+    @torch.no_grad()
+    def encode(self, x, return_z=False):
+        """VQModel.encode (vq_model.py:41-45) in eval mode: x fp32 NCHW [B,3,H,H] in [-1,1] ->
+        (quant fp32 [B,e_dim,g,g], (None, None, None, 0), (None, None, indices int64 [B*g*g])), the tuple layout of
+        VectorQuantizer.forward :255 (`_, _, [_, _, indices] = vq_model.encode(x)`, extract_codes_c2i.py:103).
+        `return_z=True` appends the pre-quantisation quant_conv output (test hook)."""
+        if not self._has_encoder_path():
+            raise NotImplementedError("encode needs encoder_ch_mult == decoder_ch_mult (true for VQ-8 and VQ-16)")
+        h = self.engine()
+        dev = self.quantize.embedding.weight.device
+        x = x.to(device=dev, dtype=torch.float32).contiguous()
+        B, C, H, W = x.shape
+        down = 2 ** (len(self.config.encoder_ch_mult) - 1)
+        if C != 3 or H != W or H % down:
+            raise ValueError(f"bad image shape {tuple(x.shape)}: need [B,3,H,H] with H a multiple of {down}")
+        g, ed = H // down, self.config.codebook_embed_dim
+        idx = torch.empty(B * g * g, dtype=torch.int64, device=dev)
+        quant = torch.empty(B, ed, g, g, dtype=torch.float32, device=dev)
+        z = torch.empty(B, ed, g, g, dtype=torch.float32, device=dev) if return_z else None
+        base, nbytes = self._workspace(h, B, g, dev)
+        _lib.check(_lib.load().lg_vq_encode(h, _lib.ptr(x), B, H, W, ctypes.c_void_p(base), nbytes, _lib.ptr(idx), _lib.ptr(quant),
+                                            _lib.ptr(z) if return_z else None, _lib.current_stream(dev)), "lg_vq_encode")
+        out = (quant, (None, None, None, 0), (None, None, idx))
+        return out + (z,) if return_z else out
 
     def decode(self, quant):
         raise NotImplementedError("use decode_code (the sampling path never calls decode on raw latents)")

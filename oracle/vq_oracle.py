@@ -4,7 +4,8 @@ Restates tokenizer/tokenizer_image/vq_model.py over a plain state_dict:
   VQModel.decode_code :52-55 -> get_codebook_entry :261-276 -> post_quant_conv :48 -> Decoder.forward :173-194
   ResnetBlock.forward :298-314, AttnBlock.forward :327-351, Upsample.forward :374-378,
   Normalize = GroupNorm(32, C, eps=1e-6) :359-362, nonlinearity (swish) :354-356,
-  VectorQuantizer.forward index path :215-233.
+  VectorQuantizer.forward index path :215-233,
+  VQModel.encode :41-45 -> Encoder.forward :100-124 (Downsample :389-397) -> quant_conv -> VectorQuantizer.forward.
 Pinned against the live reference (tests/test_oracle_vs_reference.py) and tests/golden/vq_*.pt.
 """
 from __future__ import annotations
@@ -92,3 +93,38 @@ class VQOracle:
             e = F.normalize(e, p=2, dim=-1)
         d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(e ** 2, dim=1) - 2 * (zf @ e.t())
         return torch.argmin(d, dim=1)
+
+    # ------------------------------------------------------------------ encode
+    @torch.no_grad()
+    def encode_z(self, x, ch_mult=None):                     # Encoder.forward vq_model.py:100-124 + quant_conv :42
+        ch_mult = tuple(ch_mult) if ch_mult is not None else self.ch_mult
+        h = self._conv(x, "encoder.conv_in", 1)
+        n = len(ch_mult)
+        for i in range(n):
+            for j in range(self.num_res_blocks):
+                h = self._res(h, f"encoder.conv_blocks.{i}.res.{j}")
+                if i == n - 1:                               # attention only at the coarsest level (:84-85)
+                    h = self._attn(h, f"encoder.conv_blocks.{i}.attn.{j}")
+            if i != n - 1:                                   # Downsample :389-397: pad right/bottom by one, 3x3 stride 2
+                p = f"encoder.conv_blocks.{i}.downsample.conv"
+                h = F.conv2d(F.pad(h, (0, 1, 0, 1)), self.sd[p + ".weight"], self.sd[p + ".bias"], stride=2, padding=0)
+        h = self._res(h, "encoder.mid.0")
+        h = self._attn(h, "encoder.mid.1")
+        h = self._res(h, "encoder.mid.2")
+        h = _swish(self._gn(h, "encoder.norm_out"))
+        h = self._conv(h, "encoder.conv_out", 1)
+        return self._conv(h, "quant_conv", 0)
+
+    @torch.no_grad()
+    def quantize(self, z):                                   # VectorQuantizer.forward :215-255 in eval mode
+        idx = self.argmin_indices(z)
+        zl = z.permute(0, 2, 3, 1).contiguous()
+        if self.l2_norm:
+            zl = F.normalize(zl, p=2, dim=-1)
+        zq = self.codebook()[idx].view(zl.shape)
+        zq = zl + (zq - zl)                                  # straight-through expression, kept for its fp32 rounding (:252)
+        return zq.permute(0, 3, 1, 2), idx
+
+    @torch.no_grad()
+    def encode(self, x, ch_mult=None):                       # VQModel.encode :41-45 -> (quant, indices)
+        return self.quantize(self.encode_z(x, ch_mult))

@@ -4,6 +4,7 @@ Run in the authoring container only:  python tests/golden/make_golden.py
 Outputs (committed, small):
   tests/golden/gpt_c2i.pt  gpt_t2i.pt   : state_dict + inputs + reference generate() greedy tokens and logits
   tests/golden/vq_tiny.pt               : state_dict + codes + reference decode_code pixels + argmin indices
+  tests/golden/vq_enc_tiny.pt           : encoder state_dict + image + reference z / quant / indices (VQModel.encode)
   tests/golden/sampling.pt              : logits + reference top_k_top_p_filtering / sample outputs
 Every tensor here is an output of the unmodified reference code; nothing is copied from its source.
 """
@@ -91,6 +92,27 @@ def vq_case(seed):
                 argmin=idx.clone())
 
 
+def vq_enc_case(seed):
+    """Tiny encoder (ch=32, ch_mult=(1,2), z_channels=32) + quant_conv + quantizer composed as VQModel.encode does
+    (vq_model.py:41-45)."""
+    import torch.nn as nn
+    from tokenizer.tokenizer_image.vq_model import Encoder, VectorQuantizer
+    torch.manual_seed(seed)
+    enc = Encoder(ch=32, ch_mult=(1, 2), z_channels=32).eval()
+    quant = VectorQuantizer(64, 8, 0.25, 0.0, True, True).eval()
+    qc = nn.Conv2d(32, 8, 1).eval()
+    sd = {"encoder." + k: v.clone() for k, v in enc.state_dict().items()}
+    sd["quantize.embedding.weight"] = quant.embedding.weight.data.clone()
+    sd["quant_conv.weight"] = qc.weight.data.clone()
+    sd["quant_conv.bias"] = qc.bias.data.clone()
+    x = torch.rand(2, 3, 16, 16) * 2 - 1
+    with torch.no_grad():
+        z = qc(enc(x))
+        zq, _, info = quant(z)
+    return dict(ch=32, z_channels=32, ch_mult=[1, 2], state_dict=sd, x=x, z=z.clone(), quant=zq.clone(),
+                indices=info[2].clone())
+
+
 def sampling_case(seed):
     torch.manual_seed(seed)
     V = 1024
@@ -110,6 +132,7 @@ if __name__ == "__main__":
     torch.save(gpt_case("t2i", 1), os.path.join(HERE, "gpt_t2i.pt"))
     torch.save(vq_case(2), os.path.join(HERE, "vq_tiny.pt"))
     torch.save(sampling_case(3), os.path.join(HERE, "sampling.pt"))
+    torch.save(vq_enc_case(4), os.path.join(HERE, "vq_enc_tiny.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

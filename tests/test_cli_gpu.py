@@ -38,3 +38,30 @@ def test_sample_c2i_ddp_cli_single_rank(tmp_path, monkeypatch):
     assert len(npz) == 1
     arr = np.load(tmp_path / "s" / npz[0])["arr_0"]
     assert arr.shape == (8, 256, 256, 3) and arr.dtype == np.uint8
+
+
+def test_sample_c2i_ddp_cli_resizes_to_eval_size(tmp_path, monkeypatch):
+    """--image-size 384 --image-size-eval 256: the bicubic resize of sample_c2i_ddp.py:141-142 runs inside lg_pixels_to_u8."""
+    from llamagen_b200.sample import sample_c2i_ddp
+    monkeypatch.chdir(tmp_path)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    args = sample_c2i_ddp.build_parser().parse_args(["--gpt-model", "GPT-B", "--image-size", "384", "--image-size-eval", "256",
+                                                     "--num-fid-samples", "4", "--per-proc-batch-size", "2", "--sample-dir", "s"])
+    sample_c2i_ddp.main(args)
+    npz = [f for f in os.listdir(tmp_path / "s") if f.endswith(".npz")]
+    arr = np.load(tmp_path / "s" / npz[0])["arr_0"]
+    assert arr.shape == (4, 256, 256, 3) and arr.std() > 1.0
+
+
+def test_vq_demo_cli_round_trip(tmp_path, monkeypatch):
+    """tokenizer/tokenizer_image/vq_demo.py: image -> encode -> decode_code -> <name>_<suffix>.png."""
+    from PIL import Image
+    from llamagen_b200.sample import vq_demo
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(0)
+    Image.fromarray(rng.integers(0, 255, (300, 420, 3), dtype=np.uint8)).save(tmp_path / "in.png")
+    args = vq_demo.build_parser().parse_args(["--image-path", str(tmp_path / "in.png"), "--image-size", "256", "--output-dir", "o"])
+    out = vq_demo.main(args)
+    assert out.endswith("in_tokenizer_image.png")
+    assert Image.open(out).size == (256, 256)

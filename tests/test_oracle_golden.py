@@ -39,6 +39,15 @@ def test_vq_oracle_matches_reference_golden():
     assert torch.equal(orc.argmin_indices(g["z"]), g["argmin"])
 
 
+def test_vq_encode_oracle_matches_reference_golden():
+    g = _load("vq_enc_tiny.pt")
+    orc = VQOracle(g["state_dict"], ch_mult=g["ch_mult"])
+    assert torch.equal(orc.encode_z(g["x"]), g["z"])
+    quant, idx = orc.encode(g["x"])
+    assert torch.equal(idx, g["indices"])
+    assert torch.equal(quant, g["quant"])
+
+
 @pytest.mark.parametrize("k,p", [(0, 1.0), (5, 1.0), (50, 1.0), (1024, 1.0), (0, 0.9), (100, 0.5), (1, 1.0)])
 def test_sampling_oracle_matches_reference_golden(k, p):
     g = _load("sampling.pt")

@@ -74,3 +74,32 @@ def test_vq_decode_matches_live_reference(reference_path):
     with torch.no_grad():
         ref = dec(pqc(quant.get_codebook_entry(codes, [1, 8, 3, 3], True)))
     assert torch.equal(ref, VQOracle(sd, ch_mult=(1, 2, 2)).decode_code(codes, [1, 8, 3, 3]))
+
+
+def test_vq_encode_matches_live_reference(reference_path):
+    import torch.nn as nn
+    from tokenizer.tokenizer_image.vq_model import Encoder, VectorQuantizer
+    torch.manual_seed(6)
+    enc = Encoder(ch=32, ch_mult=(1, 2, 2), z_channels=32).eval()
+    quant = VectorQuantizer(128, 8, 0.25, 0.0, True, True).eval()
+    qc = nn.Conv2d(32, 8, 1).eval()
+    sd = {"encoder." + k: v for k, v in enc.state_dict().items()}
+    sd.update({"quantize.embedding.weight": quant.embedding.weight.data, "quant_conv.weight": qc.weight.data,
+               "quant_conv.bias": qc.bias.data})
+    x = torch.rand(1, 3, 24, 16) * 2 - 1
+    with torch.no_grad():
+        zq, _, info = quant(qc(enc(x)))
+    q, idx = VQOracle(sd, ch_mult=(1, 2, 2)).encode(x)
+    assert torch.equal(idx, info[2]) and torch.equal(q, zq)
+
+
+def test_center_crop_matches_live_reference(reference_path):
+    import numpy as np
+    from PIL import Image
+    from dataset.augmentation import center_crop_arr
+    from llamagen_b200.sample.vq_demo import center_crop
+    rng = np.random.default_rng(1)
+    for shape in [(300, 420), (1100, 900), (256, 256), (513, 2000)]:
+        im = Image.fromarray(rng.integers(0, 255, (*shape, 3), dtype=np.uint8))
+        for s in (256, 384):
+            assert (np.array(center_crop(im, s)) == np.array(center_crop_arr(im, s))).all()

@@ -93,3 +93,111 @@ def test_argmin_full_codebook_vs_oracle():
         d = ((zf[bad, None, :] - e[None, :, :]) ** 2).sum(-1)
         gap = (d.gather(1, idx[bad, None]) - d.gather(1, ref[bad, None])).abs().max().item()
         assert gap <= 1e-6, gap
+
+
+# ------------------------------------------------------------------------------------------------ encode
+# Tolerance (stated): the oracle's own bf16-vs-fp32 spread on the VQ-16 encoder output z (random init, z std 0.185) is
+# max-abs 0.0145 / mean-abs 0.0029 and its argmin indices agree on 92 % of positions. We require max-abs <= 0.02 and
+# mean-abs <= 0.004 (scaled by z std / 0.185) against the fp32 oracle, >= 85 % identical indices, every differing index
+# to be a near-tie under the ORACLE's distances, and bit-exact indices given our own z (the integer part of the path).
+def _check_encode(m, x, orc):
+    quant, losses, info, z = m.encode(x.cuda(), return_z=True)
+    idx = info[2].cpu()
+    z = z.cpu()
+    assert losses == (None, None, None, 0) and info[0] is None and info[1] is None
+    z_ref = orc.encode_z(x)
+    q_ref, idx_ref = orc.quantize(z_ref)
+    scale = max(1e-3, z_ref.std().item() / 0.185)
+    err = (z - z_ref).abs()
+    assert err.max().item() <= 0.02 * scale, (err.max().item(), scale)
+    assert err.mean().item() <= 0.004 * scale, (err.mean().item(), scale)
+    # integer part: argmin of OUR z through the oracle must be bit-identical, and the returned tensor must be its quantisation
+    q_own, idx_own = orc.quantize(z)
+    assert torch.equal(idx, idx_own)
+    assert torch.allclose(quant.cpu(), q_own, atol=2e-6, rtol=0)
+    assert tuple(quant.shape) == tuple(q_ref.shape) and idx.dtype == torch.int64
+    agree = (idx == idx_ref).float().mean().item()
+    assert agree >= 0.85, agree
+    # every disagreement is a near-tie in the oracle's own distance matrix
+    e = orc.codebook()
+    zf = torch.nn.functional.normalize(z_ref.permute(0, 2, 3, 1).reshape(-1, z_ref.shape[1]), dim=-1) if orc.l2_norm \
+        else z_ref.permute(0, 2, 3, 1).reshape(-1, z_ref.shape[1])
+    d = (zf ** 2).sum(1, keepdim=True) + (e ** 2).sum(1) - 2 * zf @ e.t()
+    gap = d.gather(1, idx[:, None]) - d.gather(1, idx_ref[:, None])
+    assert gap.max().item() <= 0.2 * scale, gap.max().item()
+    return agree
+
+
+def test_tiny_encoder_matches_reference_golden():
+    g = load_golden("vq_enc_tiny.pt")
+    from llamagen_b200.vq_model import ModelArgs, VQModel
+    m = VQModel(ModelArgs(codebook_size=64, codebook_embed_dim=8, encoder_ch_mult=g["ch_mult"], decoder_ch_mult=g["ch_mult"],
+                          z_channels=g["z_channels"]), ch=g["ch"])
+    missing, unexpected = m.load_state_dict(g["state_dict"], strict=False)
+    assert not unexpected
+    m = m.cuda().eval()
+    orc = VQOracle(g["state_dict"], ch_mult=g["ch_mult"])
+    assert torch.equal(orc.encode_z(g["x"]), g["z"])            # the checker itself is pinned to the reference output
+    _check_encode(m, g["x"], orc)
+
+
+@pytest.mark.parametrize("conv", ["tcgen05", "mma"])
+@pytest.mark.parametrize("name,size,B", [("VQ-16", 256, 2), ("VQ-8", 128, 1), ("VQ-16", 384, 1)])
+def test_full_encoder_vs_oracle(name, size, B, conv, monkeypatch):
+    monkeypatch.setenv("LG_CONV_TC", "1" if conv == "tcgen05" else "0")
+    from llamagen_b200 import VQ_models
+    torch.manual_seed(size + B)
+    m = VQ_models[name](codebook_size=16384, codebook_embed_dim=8).cuda().eval()
+    x = torch.rand(B, 3, size, size) * 2 - 1
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    _check_encode(m, x, VQOracle(sd, ch_mult=m.config.encoder_ch_mult))
+
+
+def test_encode_is_batch_invariant_and_feeds_decode():
+    """extract_codes_c2i.py:103 / vq_demo.py:59-61: encode -> indices -> decode_code; images are independent."""
+    from llamagen_b200 import VQ_models
+    torch.manual_seed(3)
+    m = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).cuda().eval()
+    x = torch.rand(4, 3, 256, 256, device="cuda") * 2 - 1
+    _, _, (_, _, idx) = m.encode(x)
+    _, _, (_, _, a) = m.encode(x[:2])
+    _, _, (_, _, b) = m.encode(x[2:])
+    assert torch.equal(idx, torch.cat([a, b]))
+    pix = m.decode_code(idx.reshape(4, -1), [4, 8, 16, 16])
+    assert tuple(pix.shape) == (4, 3, 256, 256) and torch.isfinite(pix).all()
+
+
+def test_encode_rejects_bad_shapes():
+    from llamagen_b200 import VQ_models
+    m = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).cuda().eval()
+    with pytest.raises(ValueError):
+        m.encode(torch.zeros(1, 3, 250, 250))
+    with pytest.raises(ValueError):
+        m.encode(torch.zeros(1, 3, 256, 128))
+
+
+# ------------------------------------------------------------------------------------------------ pixel finishing (§8 f-1)
+def test_pixels_to_uint8_is_bit_exact():
+    from llamagen_b200.postprocess import to_uint8_nhwc
+    torch.manual_seed(0)
+    x = torch.randn(3, 3, 64, 48) * 0.8
+    x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, -1.0039216, 0.99607843])
+    ref = torch.clamp(127.5 * x + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)      # sample_c2i_ddp.py:143
+    out = to_uint8_nhwc(x.cuda()).cpu()
+    assert out.dtype == torch.uint8 and torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("src,dst", [(384, 256), (512, 256), (96, 128)])
+def test_pixels_bicubic_resize_matches_torch(src, dst):
+    """F.interpolate(mode='bicubic') of sample_c2i_ddp.py:141-142 fused with the uint8 conversion. Float tolerance: the
+    tap sums are fp32 in a different association order than ATen's, so a pixel may land on the other side of an integer
+    boundary: require |diff| <= 1 LSB everywhere and < 0.5 % of values off by one."""
+    import torch.nn.functional as F
+    from llamagen_b200.postprocess import to_uint8_nhwc
+    torch.manual_seed(src)
+    x = torch.randn(2, 3, src, src) * 0.7
+    ref = torch.clamp(127.5 * F.interpolate(x, size=(dst, dst), mode="bicubic") + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+    out = to_uint8_nhwc(x.cuda(), size=dst).cpu()
+    diff = (out.int() - ref.int()).abs()
+    assert diff.max().item() <= 1
+    assert (diff != 0).float().mean().item() < 5e-3
