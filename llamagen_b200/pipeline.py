@@ -23,14 +23,14 @@ class SamplePipeline:
         self.decode_stream = torch.cuda.Stream(device=dev)
         self._last = None
 
-    def submit(self, cond, grid: int, to_uint8_host=None):
+    def submit(self, cond, grid: int, to_uint8_host=None, emb_masks=None):
         """Enqueue generate() on the current stream and decode_code() on the decode stream. Returns the pixel tensor
         (fp32 NCHW); it is complete once `self.decode_stream` (or `wait()`) has been synchronised. When
         `to_uint8_host` (a pinned uint8 [B,H',W',3] tensor) is given, the pixel finishing of sample_c2i_ddp.py:141-143
         (bicubic resize to H' x W' when that differs from the decoder's output, clamp, uint8, NHWC — one kernel,
         postprocess.to_uint8_nhwc) and the device-to-host copy are enqueued behind the decode as well."""
         main = torch.cuda.current_stream(self.dev)
-        tokens = generate(self.gpt, cond, grid * grid, **self.kw)
+        tokens = generate(self.gpt, cond, grid * grid, emb_masks, **self.kw)
         ready = torch.cuda.Event()
         ready.record(main)
         self.decode_stream.wait_event(ready)

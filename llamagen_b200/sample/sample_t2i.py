@@ -8,10 +8,10 @@ import argparse
 import os
 import time
 
-import numpy as np
 import torch
 
 from .. import generate
+from ..cond import HFT5Encoder, load_t5_feature_files, prepare_condition, synthetic_features
 from .common import add_common_args, load_gpt, load_vq
 
 PROMPTS = [
@@ -25,28 +25,12 @@ PROMPTS = [
 def t5_features(args, device, precision):
     T, C = args.t5_feature_max_len, args.t5_feature_dim
     if args.cond_npy:
-        embs, masks = torch.zeros(len(args.cond_npy), T, C), torch.zeros(len(args.cond_npy), T)
-        for i, path in enumerate(args.cond_npy):
-            f = torch.from_numpy(np.load(path)).reshape(-1, C)[:T]
-            embs[i, : f.shape[0]] = f
-            masks[i, : f.shape[0]] = 1
+        embs, masks = load_t5_feature_files(args.cond_npy, T, C)
         return embs.to(device, precision), masks.to(device)
     if args.synthetic_cond:
-        g = torch.Generator().manual_seed(args.seed)
-        B = len(PROMPTS)
-        lens = torch.randint(8, T, (B,), generator=g)
-        masks = (torch.arange(T)[None, :] < lens[:, None]).float()
-        return (torch.randn(B, T, C, generator=g) * masks[:, :, None]).to(device, precision), masks.to(device)
+        return synthetic_features(len(PROMPTS), T, C, args.seed, device, precision)
     assert os.path.exists(args.t5_path), "--t5-path not found (use --cond-npy or --synthetic-cond without T5 weights)"
-    from transformers import AutoTokenizer, T5EncoderModel
-    path = os.path.join(args.t5_path, args.t5_model_type)
-    tok = AutoTokenizer.from_pretrained(path)
-    enc = T5EncoderModel.from_pretrained(path, torch_dtype=precision).to(device).eval()
-    t = tok(PROMPTS, max_length=T, padding="max_length", truncation=True, return_attention_mask=True,
-            add_special_tokens=True, return_tensors="pt")
-    with torch.no_grad():
-        embs = enc(input_ids=t["input_ids"].to(device), attention_mask=t["attention_mask"].to(device))["last_hidden_state"]
-    return embs.detach(), t["attention_mask"].to(device)
+    return HFT5Encoder(args.t5_path, args.t5_model_type, T, device, precision)(PROMPTS)
 
 
 def main(args):
@@ -61,16 +45,11 @@ def main(args):
     precision = gpt_model.tok_embeddings.weight.dtype
     caption_embs, emb_masks = t5_features(args, device, precision)
 
-    if not args.no_left_padding:            # sample_t2i.py:92-103: rotate valid tokens to the right end
+    if not args.no_left_padding:            # sample_t2i.py:92-103, batched on the device (cond.left_pad_features)
         print("processing left-padding...")
-        new_masks = torch.flip(emb_masks, dims=[-1])
-        rolled = []
-        for idx, (emb, m) in enumerate(zip(caption_embs, emb_masks)):
-            valid = int(m.sum().item())
-            print(f"  prompt {idx} token len: {valid}")
-            rolled.append(torch.cat([emb[valid:], emb[:valid]]))
-        caption_embs, emb_masks = torch.stack(rolled), new_masks
-    c_indices = caption_embs * emb_masks[:, :, None].to(caption_embs.dtype)
+        for idx, valid in enumerate(emb_masks.sum(dim=-1).tolist()):
+            print(f"  prompt {idx} token len: {int(valid)}")
+    c_indices, emb_masks = prepare_condition(caption_embs, emb_masks, left_padding=not args.no_left_padding)
     qzshape = [len(c_indices), args.codebook_embed_dim, latent_size, latent_size]
 
     torch.cuda.synchronize()

@@ -96,3 +96,38 @@ def test_weight_broadcast_world2_gloo():
     assert n0 == n1 and n0 > 0
     assert d0 == d1, "weights differ after the broadcast"
     assert (s0, s1) == (0, 1)
+
+
+def test_left_pad_features_matches_reference_loop():
+    """cond.left_pad_features == the per-prompt loop of sample_t2i.py:92-103 (restated here), incl. empty and full rows."""
+    import torch
+    from llamagen_b200.cond import left_pad_features, load_t5_feature_files, pack_t5_features, prepare_condition
+    torch.manual_seed(0)
+    B, T, C = 6, 12, 5
+    lens = torch.tensor([0, 1, 5, 11, 12, 7])
+    masks = (torch.arange(T)[None, :] < lens[:, None]).float()
+    embs = torch.randn(B, T, C)
+    ref_masks = torch.flip(masks, dims=[-1])
+    ref = torch.stack([torch.cat([e[int(m.sum().item()):], e[:int(m.sum().item())]]) for e, m in zip(embs, masks)])
+    out, out_masks = left_pad_features(embs, masks)
+    assert torch.equal(out, ref) and torch.equal(out_masks, ref_masks)
+    c, m = prepare_condition(embs, masks)
+    assert torch.equal(c, ref * ref_masks[:, :, None]) and torch.equal(m, ref_masks)
+    c2, m2 = prepare_condition(embs, masks, left_padding=False)
+    assert torch.equal(c2, embs * masks[:, :, None]) and torch.equal(m2, masks)
+    # extract_t5_feature.py file layout: fp32 [1, valid_len, C]; truncated at max_len
+    e, mk = pack_t5_features([torch.randn(1, 3, C).numpy(), torch.randn(1, 20, C).numpy()], max_len=T, dim=C)
+    assert e.shape == (2, T, C) and mk.sum(1).tolist() == [3.0, 12.0] and (e[0, 3:] == 0).all()
+
+
+def test_t2i_ddp_prompt_sharding(tmp_path):
+    """prompt index map of sample_t2i_ddp.py:134-138: i*world + rank + total covers every row exactly once."""
+    from llamagen_b200.sample.sample_t2i_ddp import prompt_indices, read_prompts
+    tsv = tmp_path / "p.tsv"
+    tsv.write_text("Prompt\tCategory\n" + "".join(f"prompt {i}\tc\n" for i in range(10)))
+    assert read_prompts(str(tsv)) == [f"prompt {i}" for i in range(10)]
+    world, n, seen = 2, 3, []
+    for total in (0, 6):
+        for rank in range(world):
+            seen += prompt_indices(n, rank, world, total)
+    assert sorted(seen) == list(range(12))

@@ -65,3 +65,31 @@ def test_vq_demo_cli_round_trip(tmp_path, monkeypatch):
     out = vq_demo.main(args)
     assert out.endswith("in_tokenizer_image.png")
     assert Image.open(out).size == (256, 256)
+
+
+@pytest.mark.parametrize("mode", ["synthetic", "feature-dir"])
+def test_sample_t2i_ddp_cli_single_rank(tmp_path, monkeypatch, mode):
+    """sample_t2i_ddp.py with a 5-row prompt TSV: 6 images (3 per batch, last index past the list), jsonl + captions."""
+    import json
+    from llamagen_b200.sample import sample_t2i_ddp
+    monkeypatch.chdir(tmp_path)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    (tmp_path / "parti.tsv").write_text("Prompt\tCategory\n" + "".join(f"a photo of thing {i}\tx\n" for i in range(5)))
+    extra = ["--synthetic-cond"]
+    if mode == "feature-dir":
+        os.makedirs(tmp_path / "feat")
+        rng = np.random.default_rng(0)
+        for i in range(5):
+            np.save(tmp_path / "feat" / f"{i}.npy", rng.standard_normal((1, 5 + 3 * i, 2048)).astype(np.float32))
+        extra = ["--t5-feature-dir", "feat"]
+    args = sample_t2i_ddp.build_parser().parse_args(["--gpt-model", "GPT-B", "--image-size", "256", "--prompt-csv", "parti.tsv",
+                                                     "--per-proc-batch-size", "3", "--sample-dir", "s"] + extra)
+    folder = sample_t2i_ddp.main(args)
+    pngs = sorted(os.listdir(os.path.join(folder, "images")))
+    assert pngs == [f"{i:06d}.png" for i in range(6)]
+    from PIL import Image
+    assert Image.open(os.path.join(folder, "images", pngs[0])).size == (256, 256)
+    rows = [json.loads(l) for l in open(os.path.join(folder, "result.jsonl"))]
+    assert len(rows) == 5 and rows[2]["text"] == "a photo of thing 2" and rows[2]["image_path"].endswith("000002.png")
+    assert open(os.path.join(folder, "captions.txt")).read().splitlines()[4] == "a photo of thing 4"
