@@ -131,3 +131,33 @@ def test_t2i_ddp_prompt_sharding(tmp_path):
         for rank in range(world):
             seen += prompt_indices(n, rank, world, total)
     assert sorted(seen) == list(range(12))
+
+
+def test_serve_queue_batches_and_pairs_cfg_twins(monkeypatch):
+    """Host logic of serve.LLM with the engine call stubbed: batches split at max_num_seqs and at a change of sampling
+    parameters, null-class twins mirror their conditional request, outputs come back sorted by request id."""
+    import types
+    import torch
+    from llamagen_b200 import serve
+    calls = []
+
+    def fake_generate(model, cond, max_new_tokens, **kw):
+        calls.append((cond.tolist(), max_new_tokens, kw["top_k"], kw["cfg_scale"]))
+        return cond[:, None].repeat(1, max_new_tokens)
+
+    monkeypatch.setattr(serve, "generate", fake_generate)
+    model = types.SimpleNamespace(model_type="c2i", tok_embeddings=types.SimpleNamespace(weight=torch.zeros(1)))
+    llm = serve.LLM(model, cfg_scale=4.0, num_classes=1000, max_num_seqs=2)
+    a, b = serve.SamplingParams(top_k=10, max_tokens=3), serve.SamplingParams(top_k=20, max_tokens=3)
+    labels = [5, 6, 7, 8]
+    outs = llm.generate(prompt_token_ids=[[c] for c in labels] + [[1000]] * 4, sampling_params=[a, a, a, b] * 2)
+    assert calls == [([5, 6], 3, 10, 4.0), ([7], 3, 10, 4.0), ([8], 3, 20, 4.0)]
+    assert [o.request_id for o in outs] == [str(i) for i in range(8)]
+    assert [o.outputs[0].token_ids[0] for o in outs] == labels + labels
+    assert [o.prompt_token_ids for o in outs[4:]] == [[1000]] * 4
+    assert not llm.has_unfinished_requests() and llm.get_num_unfinished_requests() == 0
+    import pytest
+    with pytest.raises(ValueError):
+        llm.generate(prompt_token_ids=[[1], [2]])
+    with pytest.raises(ValueError):
+        llm.generate(prompts=["a"], prompt_token_ids=[[1]])

@@ -93,3 +93,32 @@ def test_sample_t2i_ddp_cli_single_rank(tmp_path, monkeypatch, mode):
     rows = [json.loads(l) for l in open(os.path.join(folder, "result.jsonl"))]
     assert len(rows) == 5 and rows[2]["text"] == "a photo of thing 2" and rows[2]["image_path"].endswith("000002.png")
     assert open(os.path.join(folder, "captions.txt")).read().splitlines()[4] == "a photo of thing 4"
+
+
+def test_serve_llm_generate_matches_generate():
+    """serve.LLM (the reference's LLM.generate call surface, serve/sample_c2i.py:35-67) == generate() on the same seeds;
+    requests beyond max_num_seqs are served by later engine steps and come back sorted by request id."""
+    import torch
+    from llamagen_b200 import GPT_models, generate
+    from llamagen_b200.serve import LLM, SamplingParams
+    torch.manual_seed(0)
+    gpt = GPT_models["GPT-B"](vocab_size=16384, block_size=64, num_classes=1000, cls_token_num=1, model_type="c2i")
+    gpt = gpt.to("cuda", torch.bfloat16).eval()
+    gpt.output.weight.data.normal_(std=0.02)
+    labels = [207, 360, 387, 974, 88, 979]
+    prompts = [[c] for c in labels] + [[1000] for _ in labels]
+    sp = SamplingParams(temperature=1.0, top_p=1.0, top_k=2000, max_tokens=64)
+    llm = LLM(gpt, cfg_scale=4.0, num_classes=1000, max_num_seqs=4, seed=11)
+    outs = llm.generate(prompt_token_ids=prompts, sampling_params=sp)
+    assert [o.request_id for o in outs] == [str(i) for i in range(12)]
+    assert all(o.finished and len(o.outputs[0].token_ids) == 64 for o in outs)
+    toks = torch.tensor([o.outputs[0].token_ids for o in outs])
+    assert torch.equal(toks[:6], toks[6:])
+    dev = "cuda"
+    a = generate(gpt, torch.tensor(labels[:4], device=dev), 64, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, seed=11)
+    b = generate(gpt, torch.tensor(labels[4:], device=dev), 64, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, seed=12)
+    assert torch.equal(toks[:6], torch.cat([a, b]).cpu().long())
+    with pytest.raises(ValueError):
+        llm.generate(prompt_token_ids=[[1], [2]], sampling_params=sp)        # cfg on but no null-class twins
+    with pytest.raises(ValueError):
+        LLM(gpt, cfg_scale=1.0).generate(prompt_token_ids=[[1, 2]])
