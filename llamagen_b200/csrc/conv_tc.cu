@@ -29,6 +29,8 @@ constexpr int kATile = kPix * kCk * 2;
 struct ConvTcArgs {
     int B, Hin, Win, Cin, Hout, Wout, Cout;
     int mode;            // 0: 3x3 pad 1   1: 1x1   2: nearest-2x + 3x3 as 2x2 phase convs
+                         // 3: Downsample (vq_model.py:389-397): 3x3 stride 2 over the input zero-padded right/bottom by one
+    int Ht, Wt;          // extent of the pixel grid the patches tile: the input for modes 0-2, the output for mode 3
     int bh, bw;          // pixel patch, bh*bw == 128
     int tiles_x, tiles_y;
     int bn;              // Cout tile (multiple of 16, <= 128)
@@ -84,6 +86,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_c
                 int dy = 0, dx = 0;
                 if (a.mode == 0) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
                 else if (a.mode == 2) { const int ta = tap >> 1, tb = tap & 1; dy = py == 0 ? ta - 1 : ta; dx = px == 0 ? tb - 1 : tb; }
+                // mode 3: the map steps two input pixels per box element, so tap (ky, kx) of output patch (y0, x0) is the box
+                // at input origin (2*y0 + ky, 2*x0 + kx); the right/bottom padding is TMA's out-of-bounds zero fill
+                else if (a.mode == 3) { dy = y0 + tap / 3; dx = x0 + tap % 3; }
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 mbar_expect_tx(&full_bar[s], tx);
                 uint8_t* sa = tiles + s * stage_bytes;
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_c
         const int pix = q * 32 + lane;
         const int iy = pix / a.bw, ix = pix - iy * a.bw;
         int oy = y0 + iy, ox = x0 + ix;
-        const bool inb = oy < a.Hin && ox < a.Win;     // patches may overhang the image (TMA zero-filled the reads)
+        const bool inb = oy < a.Ht && ox < a.Wt;       // patches may overhang the image (TMA zero-filled the reads)
         if (a.mode == 2) { oy = 2 * oy + py; ox = 2 * ox + px; }
         const int cols_half = ((a.bn / 16 + 1) / 2) * 16;
         const int c_begin = half * cols_half, c_end = min(a.bn, c_begin + cols_half);
@@ -214,21 +219,25 @@ bool conv_tc_supported(int Hin, int Win, int Cin, int Cout, int ksize, int up, b
     if (Win < 8 || Hin < 8) return false;
     if (!nchw_out && Cout % 16 != 0) return false;
     if (up && ksize != 3) return false;
+    if (up == 2 && (Hin % 2 || Win % 2 || Win < 16 || Hin < 16)) return false;
     return ksize == 1 || ksize == 3;
 }
 
-// weights: up == 0 -> [Cout][k*k][Cin] bf16 ; up == 1 -> phase weights [4][Cout][4][Cin] bf16
+// weights: up == 0 or 2 (stride-2 Downsample) -> [Cout][k*k][Cin] bf16 ; up == 1 -> phase weights [4][Cout][4][Cin] bf16
 int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16* weights, const float* bias, int Cout,
                    int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st) {
     ConvTcArgs a;
     a.B = B; a.Hin = Hin; a.Win = Win; a.Cin = Cin; a.Cout = Cout;
-    a.Hout = up ? 2 * Hin : Hin; a.Wout = up ? 2 * Win : Win;
-    a.mode = up ? 2 : (ksize == 1 ? 1 : 0);
+    const bool down = up == 2;
+    up = up == 1;
+    a.Hout = up ? 2 * Hin : (down ? Hin / 2 : Hin); a.Wout = up ? 2 * Win : (down ? Win / 2 : Win);
+    a.mode = up ? 2 : (down ? 3 : (ksize == 1 ? 1 : 0));
     a.ntaps = up ? 4 : ksize * ksize;
-    a.bw = Win >= 16 ? 16 : 8;
+    a.Ht = down ? a.Hout : Hin; a.Wt = down ? a.Wout : Win;
+    a.bw = a.Wt >= 16 ? 16 : 8;
     a.bh = kPix / a.bw;
-    a.tiles_x = cdiv(Win, a.bw);
-    a.tiles_y = cdiv(Hin, a.bh);
+    a.tiles_x = cdiv(a.Wt, a.bw);
+    a.tiles_y = cdiv(a.Ht, a.bh);
     a.bn = std::min(128, ((Cout + 15) / 16) * 16);
     a.kchunks = Cin / kCk;
     a.tmem_cols = 32;
@@ -236,7 +245,8 @@ int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16*
     a.bias = bias; a.residual = residual; a.out_bf = out_bf; a.out_nchw = out_nchw;
 
     CUtensorMap amap, wmap;
-    LG_TRY(tma::make_map_nhwc(&amap, in, (uint64_t)B, (uint64_t)Hin, (uint64_t)Win, (uint64_t)Cin, (uint32_t)a.bh, (uint32_t)a.bw, kCk));
+    LG_TRY(tma::make_map_nhwc(&amap, in, (uint64_t)B, (uint64_t)Hin, (uint64_t)Win, (uint64_t)Cin, (uint32_t)a.bh, (uint32_t)a.bw, kCk,
+                              down ? 2u : 1u));
     const uint64_t wrows = (uint64_t)(up ? 4 : 1) * Cout, wcols = (uint64_t)a.ntaps * Cin;
     LG_TRY(tma::make_map_2d(&wmap, weights, wrows, wcols, wcols, (uint32_t)a.bn, kCk));
 

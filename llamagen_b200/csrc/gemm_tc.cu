@@ -275,13 +275,14 @@ int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, 
     return 0;
 }
 int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h,
-                  uint32_t box_w, uint32_t box_c) {
+                  uint32_t box_w, uint32_t box_c, uint32_t pixel_stride) {
     EncodeTiledFn enc = get_encode();
     LG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[4] = {C, W, H, B};
     cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-    cuuint32_t box[4] = {box_c, box_w, box_h, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // pixel_stride s > 1: the box traverses s*box_w x s*box_h input pixels and keeps every s-th one (a strided conv's taps)
+    cuuint32_t box[4] = {box_c, box_w * pixel_stride, box_h * pixel_stride, 1};
+    cuuint32_t estr[4] = {1, pixel_stride, pixel_stride, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -66,6 +66,6 @@ int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, 
 // host: 4-D bf16 NHWC activation [B, H, W, C]; box [1, box_h, box_w, box_c]; 128-byte swizzle; OOB -> zero
 // (signed start coordinates give the conv's zero padding for free).
 int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h,
-                  uint32_t box_w, uint32_t box_c);
+                  uint32_t box_w, uint32_t box_c, uint32_t pixel_stride = 1);
 
 }  // namespace tma

@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(128) argmin_kernel(const float* __restrict__ z
 // ------------------------------------------------------------------------------------------------ encoder front / pixel back
 // Encoder.conv_in (vq_model.py:70,101): 3x3 pad 1, 3 -> ch, evaluated in fp32 straight from the fp32 NCHW image
 // (K = 27 is far too thin for a tensor-core tile); writes the bf16 NHWC activation the rest of the encoder consumes.
-// One thread = one pixel x 8 output channels; weights are staged transposed ([tap][ch]) in shared memory.
+// One work item = 4 adjacent pixels of a row x 8 output channels (each weight read from shared memory feeds 4 pixels,
+// each input value 3 taps); the grid is persistent so the transposed weights ([tap][ch]) are staged once per CTA.
 __global__ void __launch_bounds__(256) conv_in_rgb_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                           const float* __restrict__ bias, bf16* __restrict__ out, int B, int H,
                                                           int W, int ch) {
@@ -292,39 +293,54 @@ __global__ void __launch_bounds__(256) conv_in_rgb_kernel(const float* __restric
     }
     for (int i = threadIdx.x; i < ch; i += blockDim.x) ws[27 * ch + i] = bias[i];
     __syncthreads();
-    const int oct = ch / 8;
-    const long long total = (long long)B * H * W * oct;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
-    const int o = (int)(gid % oct);
-    const long long pix = gid / oct;
-    const int xx = (int)(pix % W);
-    const int yy = (int)((pix / W) % H);
-    const int b = (int)(pix / ((long long)W * H));
-    float acc[8];
+    const int oct = ch / 8, xg = W / 4;
+    const long long total = (long long)B * H * xg * oct;
+    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(item % oct);
+        long long rest = item / oct;
+        const int x0 = (int)(rest % xg) * 4;
+        rest /= xg;
+        const int yy = (int)(rest % H);
+        const int b = (int)(rest / H);
+        float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = ws[27 * ch + o * 8 + j];
+        for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci) {
-        const float* plane = x + ((long long)b * 3 + ci) * H * W;
+            for (int j = 0; j < 8; ++j) acc[p][j] = ws[27 * ch + o * 8 + j];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int y2 = yy + ky - 1;
+        for (int ci = 0; ci < 3; ++ci) {
+            const float* plane = x + ((long long)b * 3 + ci) * H * W;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int x2 = xx + kx - 1;
-                const float v = ((unsigned)y2 < (unsigned)H && (unsigned)x2 < (unsigned)W) ? plane[(long long)y2 * W + x2] : 0.f;
-                const float* wr = ws + (ci * 9 + ky * 3 + kx) * ch + o * 8;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int y2 = yy + ky - 1;
+                float v[6];
+                const bool yok = (unsigned)y2 < (unsigned)H;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+                for (int i = 0; i < 6; ++i) {
+                    const int x2 = x0 + i - 1;
+                    v[i] = (yok && (unsigned)x2 < (unsigned)W) ? plane[(long long)y2 * W + x2] : 0.f;
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4* wr = reinterpret_cast<const float4*>(ws + (ci * 9 + ky * 3 + kx) * ch + o * 8);
+                    const float4 w0 = wr[0], w1 = wr[1];
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(v[p + kx], wv[j], acc[p][j]);
+                }
             }
         }
-    }
-    uint4 pk;
-    __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-    *reinterpret_cast<uint4*>(out + pix * ch + o * 8) = pk;
+        for (int p = 0; p < 4; ++p) {
+            uint4 pk;
+            __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p2[j] = __floats2bfloat162_rn(acc[p][2 * j], acc[p][2 * j + 1]);
+            *reinterpret_cast<uint4*>(out + (((long long)b * H + yy) * W + x0 + p) * ch + o * 8) = pk;
+        }
+    }
 }
 
 // VectorQuantizer.forward's returned tensor (vq_model.py:233,252-255): z_q = z + (e[idx] - z) with z L2-normalised
@@ -360,45 +376,89 @@ __device__ __forceinline__ void cubic_coeffs(float t, float* c) {
     c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
+// One output value: tap sums in the association order of ATen's CUDA kernel (x taps first, then y).
+__device__ __forceinline__ float pixel_value(const float* __restrict__ plane, int H, int W, bool resize, int oy, int ox, int iy, int ix,
+                                             const float* cy, const float* cx) {
+    float v;
+    if (!resize) {
+        v = plane[(long long)oy * W + ox];
+    } else {
+        v = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int yy = min(max(iy - 1 + i, 0), H - 1);
+            float r = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int xx = min(max(ix - 1 + j, 0), W - 1);
+                r += plane[(long long)yy * W + xx] * cx[j];
+            }
+            v += r * cy[i];
+        }
+    }
+    v = __fadd_rn(__fmul_rn(127.5f, v), 128.0f);
+    return fminf(fmaxf(v, 0.f), 255.f);
+}
+
+// PX output pixels per thread along x. PX = 4 with C = 3 packs the 12 output bytes into three 32-bit stores and, without
+// a resize, reads each plane with one 128-bit load; PX = 1 is the general fallback (any C, any width).
+template <int PX>
 __global__ void __launch_bounds__(256) pixels_to_u8_kernel(const float* __restrict__ in, int B, int C, int H, int W, int OH, int OW,
                                                            uint8_t* __restrict__ out) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)B * OH * OW) return;
-    const int ox = (int)(gid % OW);
-    const int oy = (int)((gid / OW) % OH);
-    const int b = (int)(gid / ((long long)OW * OH));
+    const int groups = OW / PX;
+    if (gid >= (long long)B * OH * groups) return;
+    const int ox0 = (int)(gid % groups) * PX;
+    const int oy = (int)((gid / groups) % OH);
+    const int b = (int)(gid / ((long long)groups * OH));
     const bool resize = OH != H || OW != W;
-    float cy[4], cx[4];
-    int iy = oy, ix = ox;
+    float cy[4] = {0.f, 0.f, 0.f, 0.f};
+    int iy = oy;
+    const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
     if (resize) {
-        const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
-        const float fy = sy * ((float)oy + 0.5f) - 0.5f, fx = sx * ((float)ox + 0.5f) - 0.5f;
-        iy = (int)floorf(fy); ix = (int)floorf(fx);
+        const float fy = sy * ((float)oy + 0.5f) - 0.5f;
+        iy = (int)floorf(fy);
         cubic_coeffs(fy - (float)iy, cy);
-        cubic_coeffs(fx - (float)ix, cx);
     }
-    for (int c = 0; c < C; ++c) {
-        const float* plane = in + ((long long)b * C + c) * H * W;
-        float v;
+    if (PX == 4) {
+        uint8_t bytes[12];
         if (!resize) {
-            v = plane[(long long)oy * W + ox];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(in + (((long long)b * 3 + c) * H + oy) * W + ox0);
+                const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    bytes[p * 3 + c] = (uint8_t)fminf(fmaxf(__fadd_rn(__fmul_rn(127.5f, f[p]), 128.0f), 0.f), 255.f);
+            }
         } else {
-            v = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int yy = min(max(iy - 1 + i, 0), H - 1);
-                float r = 0.f;
+            for (int p = 0; p < 4; ++p) {
+                const float fx = sx * ((float)(ox0 + p) + 0.5f) - 0.5f;
+                const int ix = (int)floorf(fx);
+                float cx[4];
+                cubic_coeffs(fx - (float)ix, cx);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int xx = min(max(ix - 1 + j, 0), W - 1);
-                    r += plane[(long long)yy * W + xx] * cx[j];
-                }
-                v += r * cy[i];
+                for (int c = 0; c < 3; ++c)
+                    bytes[p * 3 + c] = (uint8_t)pixel_value(in + ((long long)b * 3 + c) * H * W, H, W, true, oy, ox0 + p, iy, ix, cy, cx);
             }
         }
-        v = __fadd_rn(__fmul_rn(127.5f, v), 128.0f);
-        v = fminf(fmaxf(v, 0.f), 255.f);
-        out[gid * C + c] = (uint8_t)v;                       // truncation toward zero, like Tensor.to(torch.uint8)
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + (((long long)b * OH + oy) * OW + ox0) * 3);
+#pragma unroll
+        for (int w = 0; w < 3; ++w)
+            dst[w] = (uint32_t)bytes[4 * w] | ((uint32_t)bytes[4 * w + 1] << 8) | ((uint32_t)bytes[4 * w + 2] << 16) |
+                     ((uint32_t)bytes[4 * w + 3] << 24);
+    } else {
+        float cx[4] = {0.f, 0.f, 0.f, 0.f};
+        int ix = ox0;
+        if (resize) {
+            const float fx = sx * ((float)ox0 + 0.5f) - 0.5f;
+            ix = (int)floorf(fx);
+            cubic_coeffs(fx - (float)ix, cx);
+        }
+        for (int c = 0; c < C; ++c)   // truncation toward zero, like Tensor.to(torch.uint8)
+            out[(((long long)b * OH + oy) * OW + ox0) * C + c] =
+                (uint8_t)pixel_value(in + ((long long)b * C + c) * H * W, H, W, resize, oy, ox0, iy, ix, cy, cx);
     }
 }
 
@@ -572,9 +632,9 @@ int chunk_images(const lg_vq* v, int B, int g) {
 // up: 0 = same resolution, 1 = nearest-2x upsample folded in, 2 = Downsample (pad right/bottom, stride 2)
 int run_conv(const ConvW& cw, const bf16* in, int B, int Hin, int Win, int up, const bf16* residual, bf16* out_bf,
              float* out_nchw, cudaStream_t st) {
-    if (up != 2 && lg_env_flag("LG_CONV_TC", 1) && conv_tc_supported(Hin, Win, cw.cin, cw.cout, cw.k, up, out_nchw != nullptr) &&
-        (!up || cw.w_phase)) {
-        LG_PROF(PC_VQ_CONV, st, launch_conv_tc(in, B, Hin, Win, cw.cin, up ? cw.w_phase : cw.w, cw.bias, cw.cout, cw.k, up, residual,
+    if (lg_env_flag("LG_CONV_TC", 1) && conv_tc_supported(Hin, Win, cw.cin, cw.cout, cw.k, up, out_nchw != nullptr) &&
+        (up != 1 || cw.w_phase)) {
+        LG_PROF(PC_VQ_CONV, st, launch_conv_tc(in, B, Hin, Win, cw.cin, up == 1 ? cw.w_phase : cw.w, cw.bias, cw.cout, cw.k, up, residual,
                                                out_bf, out_nchw, st));
         return 0;
     }
@@ -862,7 +922,7 @@ int lg_vq_encode(lg_vq* v, const float* x_nchw, int B, int H, int W, void* dev_w
     LG_REQUIRE(((uintptr_t)dev_ws & 255) == 0, "workspace must be 256-byte aligned");
     const lg_vq_cfg& c = v->cfg;
     const int down = 1 << (c.n_mult - 1);
-    LG_REQUIRE(H == W && H > 0 && H % down == 0, "lg_vq_encode: image %dx%d must be square and a multiple of %d", H, W, down);
+    LG_REQUIRE(H == W && H > 0 && H % down == 0 && W % 4 == 0, "lg_vq_encode: image %dx%d must be square and a multiple of %d (and of 4)", H, W, down);
     const int grid = H / down, N = grid * grid, ed = c.codebook_embed_dim;
     const int Bc = chunk_images(v, B, grid);
     VqWs w = carve_vq(v, (char*)dev_ws, Bc, grid);
@@ -871,10 +931,10 @@ int lg_vq_encode(lg_vq* v, const float* x_nchw, int B, int H, int W, void* dev_w
         const int bc = std::min(Bc, B - b0);
         int h = H, wd = W;
         {
-            const long long threads = (long long)bc * h * wd * (c.ch / 8);
+            const long long items = (long long)bc * h * (wd / 4) * (c.ch / 8);
             const size_t smem = (size_t)28 * c.ch * sizeof(float);
             prof_begin(PC_VQ_CONV, st);
-            conv_in_rgb_kernel<<<(unsigned)cdiv(threads, 256), 256, smem, st>>>(x_nchw + (size_t)b0 * 3 * H * W, v->enc_in_w,
+            conv_in_rgb_kernel<<<(unsigned)std::min<long long>(cdiv(items, 256), 148 * 8), 256, smem, st>>>(x_nchw + (size_t)b0 * 3 * H * W, v->enc_in_w,
                                                                                 v->enc_in_b, w.X, bc, h, wd, c.ch);
             prof_end(st);
             LG_LAUNCH_CHECK();
@@ -912,7 +972,10 @@ int lg_pixels_to_u8(const float* in_nchw, int B, int C, int H, int W, int out_h,
     cudaStream_t st = (cudaStream_t)stream;
     LG_REQUIRE(in_nchw && out_nhwc && B > 0 && C > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "lg_pixels_to_u8: bad argument");
     const long long n = (long long)B * out_h * out_w;
-    pixels_to_u8_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(in_nchw, B, C, H, W, out_h, out_w, out_nhwc);
+    const bool vec = C == 3 && out_w % 4 == 0 && (out_w != W || out_h != H || (W % 4 == 0 && ((uintptr_t)in_nchw & 15) == 0)) &&
+                     ((uintptr_t)out_nhwc & 3) == 0;
+    if (vec) pixels_to_u8_kernel<4><<<(unsigned)cdiv(n / 4, 256), 256, 0, st>>>(in_nchw, B, C, H, W, out_h, out_w, out_nhwc);
+    else pixels_to_u8_kernel<1><<<(unsigned)cdiv(n, 256), 256, 0, st>>>(in_nchw, B, C, H, W, out_h, out_w, out_nhwc);
     LG_LAUNCH_CHECK();
     return 0;
 }

@@ -177,17 +177,18 @@ def test_encode_rejects_bad_shapes():
 
 
 # ------------------------------------------------------------------------------------------------ pixel finishing (§8 f-1)
-def test_pixels_to_uint8_is_bit_exact():
+@pytest.mark.parametrize("w", [48, 50])      # 4-pixel vector path / scalar fallback
+def test_pixels_to_uint8_is_bit_exact(w):
     from llamagen_b200.postprocess import to_uint8_nhwc
     torch.manual_seed(0)
-    x = torch.randn(3, 3, 64, 48) * 0.8
+    x = torch.randn(3, 3, 64, w) * 0.8
     x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, -1.0039216, 0.99607843])
     ref = torch.clamp(127.5 * x + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)      # sample_c2i_ddp.py:143
     out = to_uint8_nhwc(x.cuda()).cpu()
     assert out.dtype == torch.uint8 and torch.equal(out, ref)
 
 
-@pytest.mark.parametrize("src,dst", [(384, 256), (512, 256), (96, 128)])
+@pytest.mark.parametrize("src,dst", [(384, 256), (512, 256), (96, 128), (40, 30)])
 def test_pixels_bicubic_resize_matches_torch(src, dst):
     """F.interpolate(mode='bicubic') of sample_c2i_ddp.py:141-142 fused with the uint8 conversion. Float tolerance: the
     tap sums are fp32 in a different association order than ATen's, so a pixel may land on the other side of an integer
