@@ -162,14 +162,24 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        bf16* __restrict__ y, int HW, int C, int swish) {
     __shared__ float mean[32], rstd[32];
+    __shared__ float red[8][32][2];
     const int b = blockIdx.y;
+    {   // combine the per-split partials: 8 interleaved subsets in parallel, then a fixed-order sum (deterministic)
+        const int g = threadIdx.x & 31, sub = threadIdx.x >> 5;
+        float gs = 0.f, gq = 0.f;
+        for (int sp = sub; sp < splits; sp += 8) {
+            const float2 o = *reinterpret_cast<const float2*>(partial + (((size_t)b * splits + sp) * 32 + g) * 2);
+            gs += o.x;
+            gq += o.y;
+        }
+        red[sub][g][0] = gs;
+        red[sub][g][1] = gq;
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
         float gs = 0.f, gq = 0.f;
-        for (int sp = 0; sp < splits; ++sp) {
-            const float* o = partial + (((size_t)b * splits + sp) * 32 + threadIdx.x) * 2;
-            gs += o[0];
-            gq += o[1];
-        }
+#pragma unroll
+        for (int sub = 0; sub < 8; ++sub) { gs += red[sub][threadIdx.x][0]; gq += red[sub][threadIdx.x][1]; }
         const float cnt = (float)HW * (float)(C / 32);
         const float mu = gs / cnt;
         const float var = fmaxf(gq / cnt - mu * mu, 0.f);
@@ -656,7 +666,7 @@ int run_gn(const NormW& nw, const bf16* x, bf16* y, int B, int HW, int swish, fl
     gn_stats_kernel<<<dim3(splits, B), 256, 0, st>>>(x, HW, nw.c, gnbuf);
     prof_end(st);
     LG_LAUNCH_CHECK();
-    int chunks = (int)std::min<long long>(1024, std::max<long long>(1, (long long)HW * (nw.c / 8) / 1024));
+    int chunks = (int)std::min<long long>(lg_env_flag("LG_GN_CHUNKS", 256), std::max<long long>(1, (long long)HW * (nw.c / 8) / 1024));
     prof_begin(PC_VQ_GN_APPLY, st);
     gn_apply_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, gnbuf, splits, nw.gamma, nw.beta, y, HW, nw.c, swish);
     prof_end(st);
