@@ -60,23 +60,28 @@ struct AttnTmaArgs {
 // (for future steps) and attends to it straight from shared memory. Every TMA load then only touches rows written
 // in EARLIER steps, so the whole KV stream is requested before the programmatic-dependency wait and overlaps the
 // QKV GEMM; one dependent kernel per layer disappears.
-template <int HD, bool FUSED>
-__global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
+template <int HD, bool FUSED, int NST>
+__global__ void __launch_bounds__(kWarps * 32 * (NST > 2 ? NST : 1), NST > 2 ? 1 : (HD == 64 ? kCtasPerSm64 : 3)) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
                                                                const __grid_constant__ CUtensorMap vmap,
                                                                const __grid_constant__ CUtensorMap kmap16,
                                                                const __grid_constant__ CUtensorMap vmap16, AttnTmaArgs a) {
     constexpr int NSUB = HD / 64;                 // 128-byte-wide sub-tiles per row
     constexpr int SUB_BYTES = kKC * 128;          // one [kKC keys][64 dims] bf16 sub-tile
     constexpr int TILE_BYTES = NSUB * SUB_BYTES;  // K (or V) of one stage
-    constexpr int NSLOT = kWarps + (FUSED ? 1 : 0);
+    // NST > 2 (few work items, batch-1 latency path): one warp group per ring stage, so the chunks of a context are processed
+    // concurrently instead of one after the other; a stage is private to its group (named barrier, no CTA-wide sync per chunk)
+    constexpr bool PAR = NST > 2;
+    constexpr int NW = PAR ? NST * kWarps : kWarps;
+    constexpr int NSLOT = NW + (FUSED ? 1 : 0);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStagesA * 2 * TILE_BYTES);
-    float* merge = reinterpret_cast<float*>(full_bar + kStagesA);            // [NSLOT][HD + 2]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + NST * 2 * TILE_BYTES);
+    float* merge = reinterpret_cast<float*>(full_bar + NST);            // [NSLOT][HD + 2]
     bf16* qbuf = reinterpret_cast<bf16*>(merge + NSLOT * (HD + 2));            // [3][HD]: q, k_new, v_new (FUSED)
 
     const int h = blockIdx.x, r = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+    const int grp = PAR ? warp / kWarps : 0, wk = PAR ? warp % kWarps : warp;   // ring stage owned / 16-key slice inside a chunk
     const long long row0 = a.row_base + ((long long)r * a.H + h) * a.maxS;
     const int D = a.H * HD;
 
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
         prefetch_map(&vmap);
         prefetch_map(&kmap16);
         prefetch_map(&vmap16);
-        for (int s = 0; s < kStagesA; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < NST; ++s) mbar_init(&full_bar[s], 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
     const int nchunks = (nkeys + kKC - 1) / kKC;
 
     auto issue = [&](int ci) {
-        const int s = ci % kStagesA;
+        const int s = ci % NST;
         uint8_t* kt = tiles + s * 2 * TILE_BYTES;
         uint8_t* vt = kt + TILE_BYTES;
         const int row = (int)(row0 + (long long)ci * kKC);
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
             }
         }
     };
-    const int npro = min(kStagesA, nchunks);
+    const int npro = min(NST, nchunks);
     if (threadIdx.x == 0)
         for (int ci = 0; ci < npro; ++ci)
             if (FUSED || ci != nchunks - 1) issue(ci);
@@ -187,19 +192,19 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
     for (int i = 0; i < HD / 8; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
     float mx = -INFINITY, l = 0.f;
 
-    for (int ci = 0; ci < nchunks; ++ci) {
-        const int s = ci % kStagesA;
-        mbar_wait(&full_bar[s], (uint32_t)((ci / kStagesA) & 1));
+    for (int ci = grp; ci < nchunks; ci += PAR ? NST : 1) {
+        const int s = ci % NST;
+        mbar_wait(&full_bar[s], (uint32_t)((ci / NST) & 1));
         const uint32_t kt = smem_u32(tiles + s * 2 * TILE_BYTES);
         const uint32_t vt = kt + TILE_BYTES;
-        const int j0 = ci * kKC + warp * 16;          // this warp's 16 keys
+        const int j0 = ci * kKC + wk * 16;            // this warp's 16 keys
         if (j0 < nkeys) {                              // warp-uniform
             // ---- S = q K^T for 16 keys (two n8 tiles)
             float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
             for (int kk = 0; kk < HD / 16; ++kk) {
                 uint32_t b0, b1, b2, b3;
-                const int row = warp * 16 + (lane & 7) + ((lane >> 4) << 3);
+                const int row = wk * 16 + (lane & 7) + ((lane >> 4) << 3);
                 const int chunk = (kk * 2 + ((lane >> 3) & 1)) & 7;
                 ldsm_x4(kt + (kk / 4) * SUB_BYTES + swz(row, chunk), b0, b1, b2, b3);
                 mma16816(sc[0], qa[kk][0], 0u, qa[kk][1], 0u, b0, b1);
@@ -240,15 +245,22 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
 #pragma unroll
             for (int np = 0; np < HD / 16; ++np) {
                 uint32_t b0, b1, b2, b3;
-                const int row = warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                const int row = wk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
                 const int chunk = (np * 2 + (lane >> 4)) & 7;
                 ldsm_x4_t(vt + (np / 4) * SUB_BYTES + swz(row, chunk), b0, b1, b2, b3);
                 mma16816(o[2 * np], pa0, 0u, pa2, 0u, b0, b1);
                 mma16816(o[2 * np + 1], pa0, 0u, pa2, 0u, b2, b3);
             }
         }
-        __syncthreads();                                // every warp is done with stage s
-        if (threadIdx.x == 0 && ci + kStagesA < nchunks) issue(ci + kStagesA);
+        if (PAR) {
+            if (ci + NST < nchunks) {                   // uniform within the group: refill this group's stage
+                asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kWarps * 32) : "memory");
+                if (wk == 0 && lane == 0) issue(ci + NST);
+            }
+        } else {
+            __syncthreads();                            // every warp is done with stage s
+            if (threadIdx.x == 0 && ci + NST < nchunks) issue(ci + NST);
+        }
     }
 
     // ---- merge the warps (each saw a disjoint key subset) and, when FUSED, the new key held in shared memory
@@ -269,7 +281,7 @@ __global__ void __launch_bounds__(kWarps * 32, HD == 64 ? kCtasPerSm64 : 3) attn
             dot = fmaf(__bfloat162float(qbuf[e]), __bfloat162float(qbuf[HD + e]), dot);
         }
         dot = warp_sum(dot);
-        float* crow = merge + kWarps * (HD + 2);
+        float* crow = merge + NW * (HD + 2);
 #pragma unroll
         for (int i = 0; i < HD / 32; ++i) {
             const int e = lane * (HD / 32) + i;
@@ -476,19 +488,20 @@ int launch_v2(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnTmaArg
     return 0;
 }
 
-template <int HD, bool FUSED>
+template <int HD, bool FUSED, int NST = kStagesA>
 int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const CUtensorMap& kmap16, const CUtensorMap& vmap16,
              const AttnTmaArgs& a, cudaStream_t st) {
     constexpr int TILE_BYTES = (HD / 64) * kKC * 128;
-    const size_t smem = 1024 + (size_t)kStagesA * 2 * TILE_BYTES + kStagesA * sizeof(uint64_t) +
-                        (kWarps + 1) * (HD + 2) * sizeof(float) + 3 * HD * sizeof(bf16) + 16;
+    constexpr int NW = NST > 2 ? NST * kWarps : kWarps;
+    const size_t smem = 1024 + (size_t)NST * 2 * TILE_BYTES + NST * sizeof(uint64_t) +
+                        (NW + 1) * (HD + 2) * sizeof(float) + 3 * HD * sizeof(bf16) + 16;
     static bool attr = false;
     if (!attr) {
-        LG_CUDA_OK(cudaFuncSetAttribute(attn_tma_kernel<HD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LG_CUDA_OK(cudaFuncSetAttribute(attn_tma_kernel<HD, FUSED, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     dim3 grid(a.H, a.R);
-    (void)lg_launch(attn_tma_kernel<HD, FUSED>, dim3(grid), dim3(kWarps * 32), smem, st, kmap, vmap, kmap16, vmap16, a);
+    (void)lg_launch(attn_tma_kernel<HD, FUSED, NST>, dim3(grid), dim3(NW * 32), smem, st, kmap, vmap, kmap16, vmap16, a);
     LG_LAUNCH_CHECK();
     return 0;
 }
@@ -519,6 +532,9 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     const CUtensorMap& km16 = *reinterpret_cast<const CUtensorMap*>(a.kmap16);
     const CUtensorMap& vm16 = *reinterpret_cast<const CUtensorMap*>(a.vmap16);
     if (a.qkv_partial) {     // fused QKV epilogue
+        // few (row, head) items (batch-1 latency path): a 6-stage ring holds a whole 288-key context, so every K/V byte is
+        // requested before the dependency wait instead of two stages at a time
+        if (a.hd == 64 && a.R * a.H <= 2 * 148 && lg_env_flag("LG_ATTN_DEEP", 1)) return launch_t<64, true, 6>(km, vm, km16, vm16, t, st);
         if (a.hd == 64) return launch_t<64, true>(km, vm, km16, vm16, t, st);
         return launch_t<128, true>(km, vm, km16, vm16, t, st);
     }

@@ -217,6 +217,40 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
     const int R = M / Tq;
     const int dt = cfg.dtype;
     int ks = 1;
+    auto attn_args = [&](int l) {
+        AttnArgs aa;
+        aa.q = ws.q; aa.kcache = ws.kcache + (size_t)l * ws.layer_cache_bytes; aa.vcache = ws.vcache + (size_t)l * ws.layer_cache_bytes;
+        aa.out = ws.attn; aa.R = R; aa.Tq = Tq; aa.H = H; aa.hd = hd;
+        aa.maxS = ws.max_seq; aa.pos = pos; aa.emb_mask = emb_mask; aa.B = B;
+        aa.Tc = cfg.cls_token_num; aa.scale = 1.0f / sqrtf((float)hd); aa.dtype = dt;
+        if (ws.have_maps) {
+            aa.kmap = ws.kmap; aa.vmap = ws.vmap; aa.kmap16 = ws.kmap16; aa.vmap16 = ws.vmap16;
+            aa.cache_row_base = (long long)l * ws.rows * H * ws.max_seq;
+        }
+        return aa;
+    };
+    // ---- R <= 8 decode step (batch-1 latency path, gemv_small.cu): 5 dependent kernels per layer, no slabs
+    if (Tq == 1 && M <= 8 && lg_env_flag("LG_SMALL_R", 1) && lg_env_flag("LG_FUSE_QKV", 1) && attn_tma_enabled() &&
+        attn_tma_supported(attn_args(0)) && gemv_small_supported(M, 3 * D, D, dt, false) && gemv_small_supported(M, D, D, dt, false) &&
+        gemv_small_supported(M, F, D, dt, true) && gemv_small_supported(M, D, F, dt, false) && gemv_small_supported(M, V, D, dt, false)) {
+        for (int l = 0; l < L; ++l) {
+            const Layer& ly = layers[l];
+            GemvSmall gq{ly.wqkv, nullptr, 3 * D, D, M, ws.h, ly.attn_norm, cfg.norm_eps, ws.partial, nullptr, nullptr};
+            LG_PROF(PC_GEMM_QKV, st, launch_gemv_small(gq, st));
+            AttnArgs aa = attn_args(l);
+            aa.qkv_partial = ws.partial; aa.qkv_ksplit = 1; aa.freqs = freqs;
+            LG_PROF(PC_ATTENTION, st, launch_attention(aa, st));
+            GemvSmall go{ly.wo, nullptr, D, D, M, ws.attn, nullptr, 0.f, nullptr, ws.h, nullptr};
+            LG_PROF(PC_GEMM_WO, st, launch_gemv_small(go, st));
+            GemvSmall g13{ly.w1, ly.w3, F, D, M, ws.h, ly.ffn_norm, cfg.norm_eps, nullptr, nullptr, ws.ff};
+            LG_PROF(PC_GEMM_W13, st, launch_gemv_small(g13, st));
+            GemvSmall g2{ly.w2, nullptr, D, F, M, ws.ff, nullptr, 0.f, nullptr, ws.h, nullptr};
+            LG_PROF(PC_GEMM_W2, st, launch_gemv_small(g2, st));
+        }
+        GemvSmall gh{output, nullptr, V, D, M, ws.h, final_norm, cfg.norm_eps, logits_out, nullptr, nullptr};
+        LG_PROF(PC_GEMM_HEAD, st, launch_gemv_small(gh, st));
+        return 0;
+    }
     LG_PROF(PC_EMBED_MISC, st, launch_rmsnorm(ws.h, layers[0].attn_norm, ws.xn, M, D, cfg.norm_eps, dt, st));
     for (int l = 0; l < L; ++l) {
         const Layer& ly = layers[l];
@@ -231,14 +265,7 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         QkvEpiArgs qa;
         qa.partial = ws.partial; qa.ksplit = ks; qa.M = M; qa.Tq = Tq; qa.D = D; qa.H = H; qa.hd = hd;
         qa.pos = pos; qa.freqs = freqs; qa.q = ws.q; qa.kcache = kc; qa.vcache = vc; qa.maxS = ws.max_seq; qa.dtype = dt;
-        AttnArgs aa;
-        aa.q = ws.q; aa.kcache = kc; aa.vcache = vc; aa.out = ws.attn; aa.R = R; aa.Tq = Tq; aa.H = H; aa.hd = hd;
-        aa.maxS = ws.max_seq; aa.pos = pos; aa.emb_mask = emb_mask; aa.B = B;
-        aa.Tc = cfg.cls_token_num; aa.scale = 1.0f / sqrtf((float)hd); aa.dtype = dt;
-        if (ws.have_maps) {
-            aa.kmap = ws.kmap; aa.vmap = ws.vmap; aa.kmap16 = ws.kmap16; aa.vmap16 = ws.vmap16;
-            aa.cache_row_base = (long long)l * ws.rows * H * ws.max_seq;
-        }
+        AttnArgs aa = attn_args(l);
         // decode steps on the TMA path: the attention kernel is also the QKV epilogue (one dependent kernel less)
         const bool fuse_qkv = lg_env_flag("LG_FUSE_QKV", 1) && attn_tma_enabled() && attn_tma_supported(aa) &&
                               !(lg_env_flag("LG_ATTN_V2", 0) && R * H >= 4 * 148 && hd == 64);

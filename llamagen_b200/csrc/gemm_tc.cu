@@ -337,9 +337,11 @@ int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int 
 
     const int b_tile_bytes = a.rpad * kBlockK * 2;
     const int stage_bytes = kATileBytes + (a.swap ? ((b_tile_bytes + 1023) / 1024) * 1024 : kATileBytes);
-    a.stages = std::min(std::min(kMaxStages, lg_env_flag("LG_TC_STAGES", 3)), (int)((225 * 1024 - 1024) / stage_bytes));
-    // 3 stages (96 KB at R = 128) instead of filling shared memory: a CTA never owns more than ~6 k-blocks, and the
-    // smaller footprint lets the PDL-launched next kernel become resident next to this one (measured 335 -> 320 ms/step).
+    a.stages = std::min(std::min(kMaxStages, lg_env_flag("LG_TC_STAGES", 4)), (int)((225 * 1024 - 1024) / stage_bytes));
+    // 4 stages (96 KB at the R = 64 rows of a decode chain) instead of filling shared memory: a CTA never owns more than ~8
+    // k-blocks, and the smaller footprint lets the PDL-launched next kernel become resident next to this one (filling
+    // shared memory: 335 ms/step, 3 stages at R = 128: 320). With two 64-row chains, 4 stages let the QKV GEMM request its
+    // whole K range before the dependency wait: 3 -> 4 stages = 297.2 -> 294.9 ms/step (2 runs each), 5 no better.
     a.stages = std::min(a.stages, std::max(2, a.kblocks_per_split));   // never more stages than k-blocks
     a.trace = g_tc_trace;
     const bool pf = next && lg_env_flag("LG_L2_PREFETCH", 1);

@@ -123,6 +123,18 @@ bool gemm_tc_supported(int M, int N, int K, int dtype);
 int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
                     float* partial, int* ksplit_out, cudaStream_t st, const GemmNext* next = nullptr);
 
+// gemv_small.cu — decode GEMMs for R <= 8 rows: CTA-owned output columns (no split-K), RMSNorm in the prologue (normw != null),
+// epilogue by destination: out_f32 [R][N] | h (in-place residual add) | ff (SwiGLU gate of the Wa/Wb row pair)
+struct GemvSmall {
+    const void* Wa; const void* Wb;   // [N][K] bf16; Wb only for the paired (w1 | w3) form
+    int N, K, R;
+    const void* in;                   // [R][K] bf16
+    const void* normw; float eps;     // RMSNorm weight [K] or null
+    float* out_f32; void* h; void* ff;
+};
+bool gemv_small_supported(int R, int N, int K, int dtype, bool paired);
+int launch_gemv_small(const GemvSmall& g, cudaStream_t st);
+
 // *pos += 1; *step += 1  (device-side loop counters for graph replay)
 int launch_advance(int* pos, int* step, cudaStream_t st);
 int launch_set_counters(int* pos, int pos_v, int* step, int step_v, cudaStream_t st);

@@ -205,3 +205,49 @@ def test_multi_chain_decode_is_bit_identical(monkeypatch):
     for split in ("2", "4"):
         for i in range(3):
             assert torch.equal(outs[split][i], outs["1"][i]), (split, i)
+
+
+@pytest.mark.parametrize("B", [1, 3, 4])
+def test_small_row_decode_path(B, monkeypatch):
+    """R = 2B <= 8 rows take the column-owner tensor-core GEMV path (gemv_small.cu: RMSNorm in the prologue, residual /
+    SwiGLU in the epilogue, 5 kernels per layer). It must meet the same oracle bound as the batched path and agree with
+    the batched path itself (same rounding points; only fp32 summation order differs) on a teacher-forced stream."""
+    m = _registry_model("GPT-B", torch.bfloat16, 2, block_size=256, vocab_size=16384)
+    torch.manual_seed(10 + B)
+    cond = torch.randint(0, 1000, (B,))
+    monkeypatch.setenv("LG_SMALL_R", "1")
+    _bf16_parity(m, cond, 6)
+    teacher = torch.randint(0, 16384, (B, 12), generator=torch.Generator().manual_seed(B), dtype=torch.int32)
+    _, small = _gen(m, cond, 12, None, cfg_scale=4.0, teacher=teacher.clone())
+    monkeypatch.setenv("LG_SMALL_R", "0")
+    _, batched = _gen(m, cond, 12, None, cfg_scale=4.0, teacher=teacher.clone())
+    err = (small - batched).abs()
+    scale = batched.std().item()
+    assert err.max().item() <= 0.08 * scale + 0.02, (err.max().item(), scale)
+    assert err.mean().item() <= 0.01 * scale + 0.002, (err.mean().item(), scale)
+    # sampled streams are reproducible on the small-row path as well
+    monkeypatch.setenv("LG_SMALL_R", "1")
+    from llamagen_b200 import generate
+    a = generate(m, cond.cuda(), 16, cfg_scale=4.0, top_k=100, seed=3)
+    b = generate(m, cond.cuda(), 16, cfg_scale=4.0, top_k=100, seed=3)
+    assert torch.equal(a, b)
+
+
+def test_small_grid_attention_parallel_chunks_long_context(monkeypatch):
+    """Few (row, head) items take the 6-stage attention whose warp groups process the chunks of a context concurrently
+    (attn_tma.cu, NST = 6). A 400-token context (> 6 x 48 keys) also exercises the per-group stage refill. It must agree
+    with the 2-stage kernel (same arithmetic per key, different merge order) and stay greedy-identical where decisive."""
+    from llamagen_b200.gpt import ModelArgs, Transformer
+    torch.manual_seed(4)
+    m = Transformer(ModelArgs(n_layer=2, n_head=4, dim=256, block_size=400, vocab_size=1024))
+    m.output.weight.data.normal_(std=0.02)
+    m = m.to(device="cuda", dtype=torch.bfloat16).eval()
+    cond = torch.tensor([3, 7])
+    teacher = torch.randint(0, 1024, (2, 400), generator=torch.Generator().manual_seed(2), dtype=torch.int32)
+    outs = {}
+    for deep in ("1", "0"):
+        monkeypatch.setenv("LG_ATTN_DEEP", deep)
+        _, outs[deep] = _gen(m, cond, 400, None, cfg_scale=2.0, teacher=teacher.clone())
+    err = (outs["1"] - outs["0"]).abs()
+    assert err.max().item() <= BF16_TOL, err.max().item()
+    assert err.mean().item() <= BF16_TOL / 10, err.mean().item()
