@@ -45,8 +45,9 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-roofline", action="store_true")
     p.add_argument("--seed", type=int, default=0)
-    p.add_argument("--latency", action="store_true",
-                   help="extra leg: per-token decode latency at batch 1 (R=2 rows under CFG), AR sampling only")
+    p.add_argument("--latency", action="store_true", help="accepted for compatibility: the batch-1 latency leg now always runs")
+    p.add_argument("--no-latency", action="store_true",
+                   help="skip the per-token decode latency leg at batch 1 (R=2 rows under CFG, AR sampling only, < 2 s)")
     return p.parse_args()
 
 
@@ -466,8 +467,8 @@ def run_ours(args):
                                  "frac_of_floor": round((step_roof_ms * S + vq_roof_ms) / (ms / args.steps), 4),
                                  "traced_ar_kernel_ms": round(total_ms - total_vq, 2), "traced_vq_kernel_ms": round(total_vq, 2)}
 
-    # ---------------- batch-1 per-token latency (BASELINE.json metric, second half), rank 0, on request
-    if rank == 0 and args.latency:
+    # ---------------- batch-1 per-token latency (BASELINE.json metric, second half), rank 0
+    if rank == 0 and not args.no_latency:
         lab1 = torch.randint(0, 1000, (1,), device=dev)
         for _ in range(3):
             generate(gpt, lab1, S, **kw)
