@@ -251,3 +251,30 @@ def test_small_grid_attention_parallel_chunks_long_context(monkeypatch):
     err = (outs["1"] - outs["0"]).abs()
     assert err.max().item() <= BF16_TOL, err.max().item()
     assert err.mean().item() <= BF16_TOL / 10, err.mean().item()
+
+
+def test_small_row_path_t2i_masked_condition(monkeypatch):
+    """t2i decode at R = 6 rows on the small-row path: the 120-token condition prefix is masked per image (emb_masks,
+    generate.py:154-163) inside the 6-stage attention; the batched path is the reference point."""
+    from llamagen_b200.gpt import ModelArgs, Transformer
+    torch.manual_seed(8)
+    m = Transformer(ModelArgs(n_layer=3, n_head=4, dim=256, block_size=64, vocab_size=1024, cls_token_num=120, caption_dim=64,
+                              model_type="t2i"))
+    m.output.weight.data.normal_(std=0.02)
+    m = m.to(device="cuda", dtype=torch.bfloat16).eval()
+    B, S = 3, 40
+    em = torch.zeros(B, 120)
+    for b, n in enumerate((5, 61, 120)):
+        em[b, -n:] = 1                                           # left-padded: valid tokens at the right end
+    cond = (torch.randn(B, 120, 64) * em[:, :, None]).bfloat16()
+    teacher = torch.randint(0, 1024, (B, S), generator=torch.Generator().manual_seed(5), dtype=torch.int32)
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("LG_SMALL_R", flag)
+        _, outs[flag] = _gen(m, cond, S, em, cfg_scale=3.0, teacher=teacher.clone())
+    # same rounding points on both paths, different fp32 summation order; a wrong mask or row mapping would show up as an
+    # error of the order of the logit scale itself
+    err = (outs["1"] - outs["0"]).abs()
+    scale = outs["0"].std().item()
+    assert err.max().item() <= 0.2 * scale + 0.05, (err.max().item(), scale)
+    assert err.mean().item() <= 0.03 * scale + 0.005, (err.mean().item(), scale)
