@@ -56,6 +56,28 @@ __device__ __forceinline__ unsigned long long gtime() {
         if (a.trace) a.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); \
     } while (0)
 
+// ---- thread-block-cluster helpers (CLUSTER variant: the k-slices of one feature tile reduce over distributed shared memory)
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ float4 ld_peer_f4(uint32_t local_addr, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
+}
+
+// CLUSTER = false: every k-slice CTA writes its fp32 partial tile to its own slab [ks][M][N]; the consumer kernel sums the slabs.
+// CLUSTER = true (experimental, LG_TC_CLUSTER=1, not validated on hardware yet): the gridDim.y k-slice CTAs of a feature tile
+// are one thread-block cluster; each parks its partial tile in shared memory, and CTA q sums rows [q*M/ks, (q+1)*M/ks) over the
+// peers IN SLAB ORDER through DSMEM (bit-identical to the slab sum) and writes the finished fp32 tile once: out is [1][M][N].
+template <bool CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_wa,
                                                               const __grid_constant__ CUtensorMap map_wb,
                                                               const __grid_constant__ CUtensorMap map_x, TcArgs a) {
@@ -177,6 +199,48 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int n = n0 + q * 32 + lane;
         const int cols_half = ((a.rpad / 16 + 1) / 2) * 16;
         const int c_begin = half * cols_half, c_end = min(a.rpad, c_begin + cols_half);
+        if constexpr (CLUSTER) {
+            // (1) TMEM -> this CTA's fp32 tile [rpad][128] in shared memory; the operand ring is idle once tmem_full_bar fired
+            float* ctile = reinterpret_cast<float*>(tiles);
+            if (nkb > 0) {
+                mbar_wait(tmem_full_bar, 0);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                uint32_t v[16];
+                if (nkb > 0) {
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ctile[(c0 + j) * kBlockN + q * 32 + lane] = __uint_as_float(v[j]);
+            }
+            cluster_sync_all();
+            // (2) this CTA's share of the rows, summed over the peers in slab order
+            const int nct = (int)gridDim.y, rank = (int)cluster_cta_rank();
+            const int rows_per = (a.M + nct - 1) / nct;
+            const int r_begin = rank * rows_per, r_end = min(a.M, r_begin + rows_per);
+            for (int idx = threadIdx.x; idx < (r_end - r_begin) * (kBlockN / 4); idx += kThreads) {
+                const int r = r_begin + idx / (kBlockN / 4), f = (idx % (kBlockN / 4)) * 4;
+                const uint32_t la = smem_u32(ctile + r * kBlockN + f);
+                float4 acc = ld_peer_f4(la, 0u);
+                for (int pr = 1; pr < nct; ++pr) {
+                    const float4 t = ld_peer_f4(la, (uint32_t)pr);
+                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                }
+                float* o = a.partial + (size_t)r * a.N + n0 + f;
+                if (n0 + f + 3 < a.N) {
+                    *reinterpret_cast<float4*>(o) = acc;
+                } else {
+                    const float t4[4] = {acc.x, acc.y, acc.z, acc.w};
+                    for (int j = 0; j < 4; ++j)
+                        if (n0 + f + j < a.N) o[j] = t4[j];
+                }
+            }
+            cluster_sync_all();      // no CTA may retire while a peer still reads its tile
+        } else {
         float* out = a.partial + (size_t)ks * a.M * a.N;
         if (nkb > 0) {
             mbar_wait(tmem_full_bar, 0);
@@ -202,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
         } else if (n < a.N) {
             for (int r = c_begin; r < min(c_end, a.M); ++r) out[(size_t)r * a.N + n] = 0.f;
+        }
         }
     } else {
         // activations are the A operand: TMEM lane = row r, columns = 128 features -> 64-byte vector stores per thread
@@ -351,12 +416,39 @@ int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int 
     const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
     static bool attr = false;
     if (!attr) {
-        LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
     LG_REQUIRE(smem <= 227 * 1024, "gemm_tc: shared memory %zu too large", smem);
     dim3 grid(cdiv(N, kBlockN), ks);
-    (void)lg_launch(gemm_tc_kernel, dim3(grid), dim3(kThreads), smem, st, mwa, mwb, mx, a);
+    // Experimental (LG_TC_CLUSTER=1, off by default, not yet validated on hardware): on-chip split-K reduction over DSMEM,
+    // see gemm_tc_kernel<true>. Falls back to slabs when the cluster cannot be scheduled or the tile does not fit the ring.
+    if (lg_env_flag("LG_TC_CLUSTER", 0) && a.swap && ks >= 2 && ks <= 16 && N % 4 == 0 &&
+        (size_t)a.stages * stage_bytes >= (size_t)a.rpad * kBlockN * sizeof(float)) {
+        static bool cattr = false;
+        if (!cattr) {
+            LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cattr = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)ks; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = lg_pdl_enabled() ? 1 : 0;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, gemm_tc_kernel<true>, &cfg) == cudaSuccess && nclusters >= 1) {
+            if (ksplit_out) *ksplit_out = 1;
+            LG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, mwa, mwb, mx, a));
+            LG_LAUNCH_CHECK();
+            return 0;
+        }
+        (void)cudaGetLastError();
+    }
+    (void)lg_launch(gemm_tc_kernel<false>, dim3(grid), dim3(kThreads), smem, st, mwa, mwb, mx, a);
     LG_LAUNCH_CHECK();
     return 0;
 }
