@@ -6,6 +6,7 @@ named in BASELINE.json:north_star:
     Transformer.forward   autoregressive/models/gpt.py:137-257,332-382,404-430
     VQModel.decode_code   tokenizer/tokenizer_image/vq_model.py:47-55,128-194,261-378
     VectorQuantizer.forward (index path) tokenizer/tokenizer_image/vq_model.py:215-233
+    VQModel.encode        tokenizer/tokenizer_image/vq_model.py:41-45,64-124,215-255,389-397   
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
 package, and only as the checker (or the timed CPU baseline) — never as a product path.
 
