@@ -161,3 +161,36 @@ def test_serve_queue_batches_and_pairs_cfg_twins(monkeypatch):
         llm.generate(prompt_token_ids=[[1], [2]])
     with pytest.raises(ValueError):
         llm.generate(prompts=["a"], prompt_token_ids=[[1]])
+
+
+def test_left_pad_and_index_map_properties():
+    """Property checks (hypothesis): left_pad_features == per-row rotate for arbitrary ragged lengths; the DDP index map
+    i*world + rank + total (sample_c2i_ddp.py:147) is a bijection onto range(total_samples) for any world / batch."""
+    import torch
+    from hypothesis import given, settings, strategies as st
+    from llamagen_b200.cond import left_pad_features
+    from llamagen_b200.distributed import image_index
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.integers(0, 9), min_size=1, max_size=5), st.integers(0, 2 ** 31 - 1))
+    def rotate(lens, seed):
+        T, C = 9, 3
+        g = torch.Generator().manual_seed(seed)
+        embs = torch.randn(len(lens), T, C, generator=g)
+        masks = (torch.arange(T)[None, :] < torch.tensor(lens)[:, None]).float()
+        out, om = left_pad_features(embs, masks)
+        for i, n in enumerate(lens):
+            assert torch.equal(out[i], torch.roll(embs[i], shifts=-n, dims=0))
+            assert om[i].tolist() == [0.0] * (T - n) + [1.0] * n
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 8), st.integers(1, 6), st.integers(1, 4))
+    def bijection(world, n, iters):
+        seen = []
+        for it in range(iters):
+            for rank in range(world):
+                seen += [image_index(i, rank, world, it * n * world) for i in range(n)]
+        assert sorted(seen) == list(range(world * n * iters))
+
+    rotate()
+    bijection()
