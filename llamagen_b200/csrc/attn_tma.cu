@@ -472,14 +472,13 @@ int launch_v2(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnTmaArg
     constexpr int TILE_BYTES = (HD / 64) * kKC * 128;
     constexpr int WARP_BYTES = kStagesV2 * 2 * TILE_BYTES;
     const size_t smem = 1024 + (size_t)kWarpsV2 * WARP_BYTES + kWarpsV2 * kStagesV2 * sizeof(uint64_t);
-    static bool attr = false;
+    static DevOnce attr;
     static int sms = 148;
-    if (!attr) {
+    if (lg_first_on_device(attr)) {
         LG_CUDA_OK(cudaFuncSetAttribute(attn_tma_v2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        attr = true;
     }
     const int nitems = a.R * a.H;
     const int ctas = std::min(sms, (nitems + kWarpsV2 - 1) / kWarpsV2);
@@ -495,10 +494,9 @@ int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const CUtensorMap
     constexpr int NW = NST > 2 ? NST * kWarps : kWarps;
     const size_t smem = 1024 + (size_t)NST * 2 * TILE_BYTES + NST * sizeof(uint64_t) +
                         (NW + 1) * (HD + 2) * sizeof(float) + 3 * HD * sizeof(bf16) + 16;
-    static bool attr = false;
-    if (!attr) {
+    static DevOnce attr;
+    if (lg_first_on_device(attr)) {
         LG_CUDA_OK(cudaFuncSetAttribute(attn_tma_kernel<HD, FUSED, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
     }
     dim3 grid(a.H, a.R);
     (void)lg_launch(attn_tma_kernel<HD, FUSED, NST>, dim3(grid), dim3(NW * 32), smem, st, kmap, vmap, kmap16, vmap16, a);

@@ -60,6 +60,27 @@ bool lg_debug_sync();
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Function attributes (dynamic shared memory opt-in, cluster size) are per device: one bit per device ordinal.
+struct DevOnce { std::atomic<uint32_t> mask{0}; };
+inline bool lg_first_on_device(DevOnce& o) {
+    int d = 0;
+    cudaGetDevice(&d);
+    const uint32_t bit = 1u << (d & 31);
+    return (o.mask.fetch_or(bit) & bit) == 0;
+}
+// Every extern "C" entry point that launches, allocates or records events runs on the engine's own device, whatever the
+// caller's current device is (one process may hold engines on several GPUs).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL): every kernel of the decode step is launched with
 // programmaticStreamSerializationAllowed so its CTAs are scheduled (and run their prologue) while the

@@ -253,10 +253,9 @@ int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16*
     const int b_tile_bytes = a.bn * kCk * 2;
     const int stage_bytes = kATile + ((b_tile_bytes + 1023) / 1024) * 1024;
     const size_t smem = 1024 + (size_t)kConvStages * stage_bytes + (2 * kConvStages + 1) * sizeof(uint64_t) + 16;
-    static bool attr = false;
-    if (!attr) {
+    static DevOnce attr;
+    if (lg_first_on_device(attr)) {
         LG_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        attr = true;
     }
     LG_REQUIRE(smem <= 110 * 1024, "conv_tc: shared memory %zu too large", smem);
     dim3 grid((unsigned)(B * a.tiles_x * a.tiles_y), (unsigned)cdiv(Cout, a.bn), up ? 4 : 1);

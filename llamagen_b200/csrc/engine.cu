@@ -143,6 +143,7 @@ struct lg_engine {
     Workspace full, sub[kMaxChains];      // sub[g]: rows/n_sub each, carved INSIDE the regions of `full` (multi-chain decode)
     int n_sub = 0;                        // 0: no split available
     bool use_graph = true;
+    bool ws_needs_zero = false;           // KV cache + counters of `full` still have to be zero-filled (done on the caller's stream)
     cudaStream_t works[kMaxChains] = {nullptr, nullptr, nullptr, nullptr};   // engine-owned streams (one per chain)
     cudaEvent_t ev_fork = nullptr, ev_joins[kMaxChains] = {nullptr, nullptr, nullptr, nullptr};
     ~lg_engine() {
@@ -154,6 +155,13 @@ struct lg_engine {
     }
 
     size_t carve(Workspace& o, char* base, int rows, int max_seq) const;
+    int zero_fill_if_needed(cudaStream_t st) {
+        if (!ws_needs_zero || !full.base) return 0;
+        LG_CUDA_OK(cudaMemsetAsync(full.kcache, 0, 2 * ((full.layer_cache_bytes * cfg.n_layer + 255) / 256 * 256), st));
+        LG_CUDA_OK(cudaMemsetAsync(full.counters, 0, 128 * sizeof(int), st));
+        ws_needs_zero = false;
+        return 0;
+    }
     int forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, float* logits_out, bool round_out,
                 cudaStream_t st);
     int embed_cond(const void* cond, int B, int R, int T, cudaStream_t st);
@@ -205,8 +213,12 @@ size_t lg_engine::carve(Workspace& o, char* base, int rows, int max_seq) const {
 int lg_engine::gemm(const void* x, int M, int N, int K, const void* wa, const void* wb, int n_split, int* ksplit,
                     float* direct_out, cudaStream_t st, const GemmNext* next) {
     // when the plan needs a single slab the GEMM can write straight into `direct_out`
-    const size_t slabs = gemm_partial_floats(M, N, K, cfg.dtype) / ((size_t)M * N);
+    const size_t need = gemm_partial_floats(M, N, K, cfg.dtype);
+    const size_t slabs = need / ((size_t)M * N);
     float* dst = (direct_out && slabs == 1) ? direct_out : ws.partial;
+    // the plan (k-slices) is not monotone in M and depends on run-time switches: never trust the carve-time sizing blindly
+    LG_REQUIRE(dst == direct_out || need <= ws.partial_floats, "gemm %dx%dx%d needs %zu partial floats, workspace holds %zu", M, N, K, need,
+               ws.partial_floats);
     GemmPlan plan;
     LG_TRY(gemm_partial(x, K, wa, wb, n_split, M, N, K, cfg.dtype, dst, &plan, st, next));
     *ksplit = plan.ksplit;
@@ -372,7 +384,11 @@ int lg_engine_create(const lg_model_cfg* cfg, int device, lg_engine** out) {
     return 0;
 }
 
-void lg_engine_destroy(lg_engine* e) { delete e; }
+void lg_engine_destroy(lg_engine* e) {
+    if (!e) return;
+    DeviceGuard guard(e->device);
+    delete e;
+}
 
 int lg_engine_bind_weight(lg_engine* e, const char* name, const void* dev_ptr, const int64_t* shape, int ndim,
                           int dtype) {
@@ -451,6 +467,7 @@ int lg_engine_workspace_bytes(lg_engine* e, int rows, int max_seq, size_t* bytes
 
 int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, int max_seq) {
     LG_REQUIRE(e && dev_ws, "lg_engine_set_workspace: null argument");
+    DeviceGuard guard(e->device);
     LG_REQUIRE(((uintptr_t)dev_ws & 255) == 0, "workspace must be 256-byte aligned");
     Workspace tmp;
     const size_t needb = e->carve(tmp, (char*)dev_ws, rows, max_seq);
@@ -459,8 +476,10 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
     tmp.bytes = bytes;
     // The reference zero-fills the KV cache (gpt.py:174-175). The tensor-core attention multiplies masked
     // probabilities (exactly 0) with whatever sits in not-yet-written V rows, so those rows must be finite.
-    LG_CUDA_OK(cudaMemset(tmp.kcache, 0, 2 * ((tmp.layer_cache_bytes * e->cfg.n_layer + 255) / 256 * 256)));
-    LG_CUDA_OK(cudaMemset(tmp.counters, 0, 128 * sizeof(int)));
+    // The zero-fill is enqueued on the CALLER'S stream by the first prefill / decode / generate that uses this workspace
+    // (zero_fill_if_needed): a legacy-NULL-stream memset here would not be ordered against non-blocking streams that may
+    // still be running kernels on memory the caching allocator has just recycled.
+    e->ws_needs_zero = true;
     tmp.have_maps = false;
     if (e->cfg.dtype == LG_DTYPE_BF16 && (e->hd == 64 || e->hd == 128)) {
         const long long total_rows = (long long)e->cfg.n_layer * rows * e->cfg.n_head * max_seq;
@@ -538,7 +557,10 @@ int lg_prefill(lg_engine* e, const void* cond, const float* emb_mask, int B, int
                void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int R = use_cfg ? 2 * B : B;
+    LG_REQUIRE(e, "lg_prefill: null engine");
+    DeviceGuard guard(e->device);
     LG_TRY(check_ready(e, R, T));
+    LG_TRY(e->zero_fill_if_needed(st));
     LG_REQUIRE(cond && logits_out && B > 0, "lg_prefill: bad argument");
     LG_REQUIRE(T == e->cfg.cls_token_num, "lg_prefill: T=%d must equal cls_token_num=%d", T, e->cfg.cls_token_num);
     LG_TRY(e->embed_cond(cond, B, R, T, st));
@@ -551,7 +573,10 @@ int lg_prefill(lg_engine* e, const void* cond, const float* emb_mask, int B, int
 int lg_decode_step(lg_engine* e, const int32_t* tokens, int B, int pos, int use_cfg, float* logits_out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int R = use_cfg ? 2 * B : B;
+    LG_REQUIRE(e, "lg_decode_step: null engine");
+    DeviceGuard guard(e->device);
     LG_TRY(check_ready(e, R, pos + 1));
+    LG_TRY(e->zero_fill_if_needed(st));
     LG_REQUIRE(tokens && logits_out && B > 0 && pos >= 0, "lg_decode_step: bad argument");
     LG_TRY(launch_embed(e->tok_emb, tokens, B, R, -1, e->cfg.dim, e->cfg.dtype, e->ws.h, st));
     PosArg p{nullptr, pos};
@@ -582,6 +607,7 @@ int lg_generate(lg_engine* e, const void* cond, const float* emb_mask, int B, in
     // into a CUDA graph. Semantics for the caller stay "asynchronous on the given stream".
     cudaStream_t caller = (cudaStream_t)stream;
     LG_REQUIRE(e, "lg_generate: null engine");
+    DeviceGuard guard(e->device);
     if (!e->works[0]) {
         for (int i = 0; i < lg_engine::kMaxChains; ++i) {
             LG_CUDA_OK(cudaStreamCreateWithFlags(&e->works[i], cudaStreamNonBlocking));
@@ -589,6 +615,7 @@ int lg_generate(lg_engine* e, const void* cond, const float* emb_mask, int B, in
         }
         LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     }
+    LG_TRY(e->zero_fill_if_needed(caller));
     LG_CUDA_OK(cudaEventRecord(e->ev_fork, caller));
     for (int i = 0; i < lg_engine::kMaxChains; ++i) LG_CUDA_OK(cudaStreamWaitEvent(e->works[i], e->ev_fork, 0));
     const int rc = generate_impl(e, cond, emb_mask, B, T, S, sc, out_tokens, dbg_logits, teacher, e->works[0]);

@@ -143,10 +143,9 @@ int gemm_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_s
         LG_REQUIRE(grid.y <= 65535, "gemm: too many rows for the skinny path (%d)", M);
         if (dtype == LG_DTYPE_F32) {
             const size_t smem = (size_t)kSkinnyRT * kSkinnyKC * sizeof(float);
-            static bool attr = false;
-            if (!attr) {
+            static DevOnce attr;
+            if (lg_first_on_device(attr)) {
                 LG_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr = true;
             }
             (void)lg_launch(gemm_skinny_kernel<float>, dim3(grid), dim3(kSkinnyWarps * 32), smem, st, 
                 (const float*)X, ldx, (const float*)Wa, (const float*)Wb, n_split, M, N, K, kper, partial);

@@ -231,10 +231,9 @@ int launch_gemm_mma(const AL& al, const BRows& bw, int M, int N, int K, int kspl
                     cudaStream_t st) {
     auto kern = gemm_mma_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, AL, Epi>;
     constexpr int smem = STAGES * (BM + BN) * 128;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DevOnce attr_set;
+    if (lg_first_on_device(attr_set)) {
         LG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
     LG_REQUIRE(K % 8 == 0, "gemm: K=%d must be a multiple of 8", K);
     const int kt_total = (K + BK - 1) / BK;

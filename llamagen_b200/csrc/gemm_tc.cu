@@ -539,10 +539,9 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
     a.pf1 = pf ? (const char*)next->p1 : nullptr; a.pfb1 = pf ? next->b1 : 0;
     LG_REQUIRE(a.stages >= 2, "gemm_tc: tile too large for a 2-stage ring");
     const size_t smem = 1024 + (size_t)a.stages * stage_bytes + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
-    static bool attr = false;
-    if (!attr) {
+    static DevOnce attr;
+    if (lg_first_on_device(attr)) {
         LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
     }
     LG_REQUIRE(smem <= 227 * 1024, "gemm_tc: shared memory %zu too large", smem);
     dim3 grid(cdiv(N, kBlockN), ks);
@@ -553,11 +552,10 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
                       (size_t)a.stages * stage_bytes >= (size_t)a.rpad * kBlockN * sizeof(float) &&
                       (!fuse || fuse->epi == 0 || (N % kBlockN == 0 && (!pair || (n_split * 2 == N && n_split % kBlockN == 0))));
     if ((fuse || lg_env_flag("LG_TC_CLUSTER", 0) == 1) && fits) {
-        static bool cattr = false;
-        if (!cattr) {
+        static DevOnce cattr;
+        if (lg_first_on_device(cattr)) {
             LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            cattr = true;
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;

@@ -224,10 +224,9 @@ template <int ROWS, int PF>
 int launch_t(const GemvArgs& a, cudaStream_t st) {
     constexpr int MT = ROWS == 32 ? 2 : 1;
     const size_t smem = (size_t)(kWarps * MT * 16 * 8 + 64) * sizeof(float) + (size_t)a.R * (a.K * 2 + 16);
-    static bool attr = false;
-    if (!attr) {
+    static DevOnce attr;
+    if (lg_first_on_device(attr)) {
         LG_CUDA_OK(cudaFuncSetAttribute(gemv_small_kernel<ROWS, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr = true;
     }
     LG_REQUIRE(smem <= 100 * 1024, "gemv_small: %zu bytes of shared memory (R=%d K=%d)", smem, a.R, a.K);
     const int rows_per_cta = a.Wb ? 16 : ROWS;

@@ -342,10 +342,9 @@ int launch_sample(const SampleArgs& a, cudaStream_t st) {
     LG_REQUIRE(a.B > 0 && a.V > 0, "lg_sample: bad shape B=%d V=%d", a.B, a.V);
     const size_t smem = (size_t)a.V * sizeof(float);
     LG_REQUIRE(smem <= 200 * 1024, "lg_sample: vocab %d too large for the shared-memory row stage", a.V);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DevOnce attr_set;
+    if (lg_first_on_device(attr_set)) {
         LG_CUDA_OK(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
     }
     (void)lg_launch(sample_kernel, dim3(a.B), dim3(kSampleThreads), smem, st, a);
     LG_LAUNCH_CHECK();

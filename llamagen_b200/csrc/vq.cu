@@ -750,7 +750,11 @@ int lg_vq_create(const lg_vq_cfg* cfg, int device, lg_vq** out) {
     return 0;
 }
 
-void lg_vq_destroy(lg_vq* v) { delete v; }
+void lg_vq_destroy(lg_vq* v) {
+    if (!v) return;
+    DeviceGuard guard(v->device);
+    delete v;
+}
 
 int lg_vq_bind_weight(lg_vq* v, const char* name, const void* dev_ptr, const int64_t* shape, int ndim) {
     LG_REQUIRE(v && name && dev_ptr && shape && ndim >= 1 && ndim <= 4, "lg_vq_bind_weight: bad argument");
@@ -766,6 +770,7 @@ int lg_vq_bind_weight(lg_vq* v, const char* name, const void* dev_ptr, const int
 int lg_vq_finalize(lg_vq* v, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LG_REQUIRE(v, "null vq");
+    DeviceGuard guard(v->device);
     for (void* p : v->owned) cudaFree(p);
     v->owned.clear();
     v->levels.clear();
@@ -865,6 +870,7 @@ int lg_vq_workspace_bytes(lg_vq* v, int B, int grid, size_t* bytes) {
 int lg_vq_decode(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws, size_t ws_bytes, float* out_nchw, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LG_REQUIRE(v && v->finalized, "vq engine not finalized");
+    DeviceGuard guard(v->device);
     LG_REQUIRE(codes && dev_ws && out_nchw && B > 0 && grid > 0, "lg_vq_decode: bad argument");
     LG_REQUIRE(((uintptr_t)dev_ws & 255) == 0, "workspace must be 256-byte aligned");
     const lg_vq_cfg& c = v->cfg;
@@ -904,14 +910,15 @@ int lg_vq_decode(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws, 
 int lg_vq_argmin(lg_vq* v, const float* z_nchw, int B, int grid, int64_t* out_idx, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LG_REQUIRE(v && v->finalized, "vq engine not finalized");
+    DeviceGuard guard(v->device);
     LG_REQUIRE(z_nchw && out_idx && B > 0 && grid > 0, "lg_vq_argmin: bad argument");
     const lg_vq_cfg& c = v->cfg;
     const int nz = B * grid * grid, ed = c.codebook_embed_dim;
     const size_t smem = (size_t)kArgminTile * (ed + 1) * sizeof(float);
 #define LG_ARGMIN(ED)                                                                                              \
     do {                                                                                                           \
-        static bool attr = false;                                                                                  \
-        if (!attr) { LG_CUDA_OK(cudaFuncSetAttribute(argmin_kernel<ED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kArgminTile * (ED + 1) * 4))); attr = true; } \
+        static DevOnce attr;                                                                                  \
+        if (lg_first_on_device(attr)) { LG_CUDA_OK(cudaFuncSetAttribute(argmin_kernel<ED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kArgminTile * (ED + 1) * 4))); } \
         argmin_kernel<ED><<<cdiv(nz, 128), 128, smem, st>>>(z_nchw, B, grid, v->codebook, v->codebook_sq, c.codebook_size, c.l2_norm, out_idx); \
     } while (0)
     if (ed == 8) LG_ARGMIN(8);
@@ -927,6 +934,7 @@ int lg_vq_encode(lg_vq* v, const float* x_nchw, int B, int H, int W, void* dev_w
                  float* out_quant_nchw, float* out_z_nchw, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LG_REQUIRE(v && v->finalized, "vq engine not finalized");
+    DeviceGuard guard(v->device);
     LG_REQUIRE(v->has_encoder, "lg_vq_encode: encoder.* / quant_conv.* weights were not bound");
     LG_REQUIRE(x_nchw && dev_ws && out_idx && B > 0, "lg_vq_encode: bad argument");
     LG_REQUIRE(((uintptr_t)dev_ws & 255) == 0, "workspace must be 256-byte aligned");

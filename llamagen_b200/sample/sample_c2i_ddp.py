@@ -46,7 +46,14 @@ def main(args):
         print(f"broadcast {nbytes / 1e6:.1f} MB of weights over NCCL")
     torch.manual_seed(seed)
 
-    folder = (f"{args.gpt_model}-size-{args.image_size}-size-{args.image_size_eval}-{args.vq_model}-topk-{args.top_k}-topp-{args.top_p}-"
+    # folder name of sample_c2i_ddp.py:100-107 (model, checkpoint name, sizes, sampling knobs); "random-init" when no ckpt is given
+    model_name = args.gpt_model.replace("/", "-")
+    ckpt = args.gpt_ckpt or "random-init"
+    if getattr(args, "from_fsdp", False) and args.gpt_ckpt and len(args.gpt_ckpt.split("/")) > 1:
+        ckpt_name = args.gpt_ckpt.split("/")[-2]
+    else:
+        ckpt_name = os.path.basename(ckpt).replace(".pth", "").replace(".pt", "")
+    folder = (f"{model_name}-{ckpt_name}-size-{args.image_size}-size-{args.image_size_eval}-{args.vq_model}-topk-{args.top_k}-topp-{args.top_p}-"
               f"temperature-{args.temperature}-cfg-{args.cfg_scale}-seed-{args.global_seed}")
     sample_folder_dir = f"{args.sample_dir}/{folder}"
     if rank == 0:

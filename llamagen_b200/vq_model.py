@@ -169,7 +169,9 @@ class VQModel(nn.Module):
         if first.dtype != torch.float32:
             raise _lib.LgError("the VQ tokenizer is kept in fp32 like the reference (sample_c2i.py:30); "
                                "weights are repacked to bf16 operands inside the engine")
-        sig = (first.device, tuple(t.data_ptr() for t in tensors.values()))
+        # lg_vq_finalize repacks the conv weights and the normalised codebook into engine-owned copies, so an in-place
+        # update (load_state_dict, broadcast_module's copy_) must rebuild them: the version counters are part of the key
+        sig = (first.device, tuple((t.data_ptr(), t._version) for t in tensors.values()))
         if self._handle is not None and sig == self._sig:
             return self._handle
         self._drop()
@@ -182,7 +184,9 @@ class VQModel(nn.Module):
         dev = first.device.index if first.device.index is not None else torch.cuda.current_device()
         _lib.check(lib.lg_vq_create(ctypes.byref(cfg), dev, ctypes.byref(h)), "lg_vq_create")
         for name, t in tensors.items():
-            _lib.check(lib.lg_vq_bind_weight(h, name.encode(), _lib.ptr(t.contiguous()), _lib.shape_array(t.shape), t.dim()),
+            if not t.is_contiguous():          # a .contiguous() temporary would leave the engine with a dangling pointer
+                raise _lib.LgError(f"parameter {name} must be contiguous")
+            _lib.check(lib.lg_vq_bind_weight(h, name.encode(), _lib.ptr(t), _lib.shape_array(t.shape), t.dim()),
                        f"bind {name}")
         _lib.check(lib.lg_vq_finalize(h, _lib.current_stream(first.device)), "lg_vq_finalize")
         self._handle, self._sig = h, sig
