@@ -36,7 +36,7 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    p.add_argument("--impl", choices=["ours", "reference", "gpu-reference"], default="ours")
     p.add_argument("--gpt-model", default="GPT-L")
     p.add_argument("--image-size", type=int, default=256)
     p.add_argument("--batch", type=int, default=64, help="images per GPU per step")
@@ -44,6 +44,10 @@ def parse():
     p.add_argument("--top-k", type=int, default=2000)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-roofline", action="store_true")
+    p.add_argument("--no-gpu-reference", action="store_true",
+                   help="skip the leg that times the reference's PyTorch-GPU path (oracle port, bf16, eager + torch.compile) on this GPU")
+    p.add_argument("--gpu-reference-batches", default="64,32", help="per-GPU batch sizes of the gpu_reference leg (first = --batch)")
+    p.add_argument("--no-operating-points", action="store_true", help="skip the extra B=32 (north_star B=256 / 8 GPUs) timing of our arm")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--latency", action="store_true", help="accepted for compatibility: the batch-1 latency leg now always runs")
     p.add_argument("--no-latency", action="store_true",
@@ -143,13 +147,14 @@ def algorithmic(name, R, S, T=1, V=16384):
     kv_write = 4 * L * R * D
     step_bytes = w_bytes + kv_read + kv_write + 4 * R * V
     step_flops = 2 * R * (L * (4 * D * D + 3 * D * F) + D * V) + 4 * L * R * D * cbar
-    per_launch = {   # bytes one launch of each kernel class must move (weights + activations in/out)
+    per_launch = {   # SURVEY §8(d) algorithmic bytes one launch must move: weights (+ fp32 logits once); activations and
+        # split-K partials live in L2 and are NOT counted (the r1 line counted them and over-stated frac)
         "attention": 4 * R * D * cbar + 4 * R * D,
-        "gemm_qkv": 2 * 3 * D * D + 2 * R * D + 4 * R * 3 * D,
-        "gemm_wo": 2 * D * D + 2 * R * D + 4 * R * D,
-        "gemm_w13": 2 * 2 * F * D + 2 * R * D + 4 * R * 2 * F,
-        "gemm_w2": 2 * D * F + 2 * R * F + 4 * R * D,
-        "gemm_head": 2 * V * D + 2 * R * D + 4 * R * V,
+        "gemm_qkv": 2 * 3 * D * D,
+        "gemm_wo": 2 * D * D,
+        "gemm_w13": 2 * 2 * F * D,
+        "gemm_w2": 2 * D * F,
+        "gemm_head": 2 * V * D + 4 * R * V,
     }
     per_launch_flops = {"gemm_qkv": 2 * R * 3 * D * D, "gemm_wo": 2 * R * D * D, "gemm_w13": 2 * R * 2 * F * D,
                         "gemm_w2": 2 * R * D * F, "gemm_head": 2 * R * V * D, "attention": 4 * R * D * cbar}
@@ -164,8 +169,10 @@ def kernel_class(name: str) -> str:
         return "vq_conv_gemm"
     if "EpiVq" in n or "softmax_rows" in n:
         return "vq_attn"
-    if "gemm_tc_kernel" in n or "gemm_skinny" in n or "gemm_mma_kernel" in n:
+    if "gemm_tc" in n or "gemm_skinny" in n or "gemm_mma_kernel" in n or "gemv_small" in n:
         return "dense_gemm"
+    if "decode_small" in n:
+        return "persistent_decode"
     for key, cls in (("residual_norm", "residual_rmsnorm"), ("qkv_epilogue", "qkv_rope_kvwrite"), ("silu_mul", "silu_mul"),
                      ("sample_kernel", "sample"), ("gn_stats", "vq_gn_stats"), ("gn_apply", "vq_gn_apply"),
                      ("lookup_postquant", "vq_misc")):
@@ -272,6 +279,45 @@ def run_reference(args, rank):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------- GPU reference leg
+def run_gpu_reference(args):
+    """The reference's own PyTorch path on THIS GPU: oracle port (bit-identical to the live reference, takes
+    device tensors), bf16 GPT + fp32/TF32 VQ decode, eager and torch.compile(mode="reduce-overhead", fullgraph=True), same
+    batch / cfg / top-k / tokens as our arm, CUDA-event timed. See oracle/gpu_baseline.py."""
+    import torch
+    from llamagen_b200 import GPT_models, VQ_models
+    from oracle import gpu_baseline
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    g = args.image_size // 16
+    S = g * g
+    torch.manual_seed(args.seed)
+    gpt = GPT_models[args.gpt_model](block_size=S, vocab_size=16384)
+    gpt.output.weight.data.normal_(std=0.02)
+    c = gpt.config
+    cfg = dict(n_layer=c.n_layer, n_head=c.n_head, dim=c.dim, norm_eps=c.norm_eps, rope_base=c.rope_base, num_classes=c.num_classes,
+               cls_token_num=1, block_size=S, model_type="c2i")
+    gsd = {k: v.detach().to(device=dev, dtype=torch.bfloat16 if v.is_floating_point() else v.dtype) for k, v in gpt.state_dict().items()}
+    vq = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8)
+    vsd = {k: v.detach().to(dev) for k, v in vq.state_dict().items()}
+    out = {"kind": "oracle port of the reference (pinned bit-identical to it), torch " + torch.__version__,
+           "precision": "bf16 GPT, fp32 VQ decode with TF32 allowed (sample_c2i.py:4-6,30,38)",
+           "timing": "CUDA events around generate()+decode_code(), synchronised both sides", "batches": {}}
+    t0 = time.time()
+    for b in [int(x) for x in args.gpu_reference_batches.split(",") if x]:
+        left = 780.0 - (time.time() - t0)
+        if left < 60:
+            out["batches"][str(b)] = {"skipped": "time budget of the leg exhausted"}
+            continue
+        try:
+            out["batches"][str(b)] = gpu_baseline.measure(gsd, cfg, vsd, b, S, g, args.cfg_scale, args.top_k, do_compile=True, log=log,
+                                                          budget_s=left - 30)
+        except Exception as ex:
+            out["batches"][str(b)] = {"error": f"{type(ex).__name__}: {str(ex)[-300:]}"}
+        torch.cuda.empty_cache()
+    emit({"impl": "gpu-reference", "gpu_reference": out})
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -386,7 +432,11 @@ def run_ours(args):
     if rank == 0 and not args.no_roofline:
         pk = peaks()
         log("roofline leg: tracing one step (CUPTI kernel timestamps)")
-        lib.lg_set_pdl(0)        # additive kernel durations: nothing starts early and waits on its dependency
+        # Additive, isolated kernel durations: PDL off (nothing starts early and waits on its dependency) and ONE decode chain
+        # (with two chains the kernels of both run concurrently, share the SMs and summed CUPTI durations exceed wall time).
+        lib.lg_set_pdl(0)
+        split_env = os.environ.get("LG_SPLIT")
+        os.environ["LG_SPLIT"] = "1"
         step_resident(labels_dev)
         pipe.wait()
         torch.cuda.synchronize()
@@ -394,8 +444,18 @@ def run_ours(args):
         def traced():
             step_resident(labels_dev)
             pipe.wait()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        traced()
+        ev1.record()
+        torch.cuda.synchronize()
+        traced_wall_ms = ev0.elapsed_time(ev1)
         classes = trace_classes(traced, dev)
         lib.lg_set_pdl(1 if os.environ.get("LG_PDL", "1") != "0" else 0)
+        if split_env is None:
+            del os.environ["LG_SPLIT"]
+        else:
+            os.environ["LG_SPLIT"] = split_env
         if classes is None:      # CUPTI unavailable: event-bracketed launches through the library's own profiler
             lib.lg_profile_reset()
             lib.lg_profile_enable(1)
@@ -452,7 +512,9 @@ def run_ours(args):
                 line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                     "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"],
                                     "algorithmic_bytes_per_launch": work[dom]["bytes"] / v["launches"],
-                                    "avg_launch_us": 1000.0 * v["total_ms"] / v["launches"], "timing": timing_source + "; traced with PDL off so durations are additive"}
+                                    "avg_launch_us": 1000.0 * v["total_ms"] / v["launches"],
+                                    "timing": timing_source + "; traced with PDL off and a single decode chain so durations are additive and isolated",
+                                    "algorithmic_bytes": "SURVEY 8(d): weight bytes of the GEMM (+ fp32 logits for the head); no activations, no split-K partials"}
             else:
                 ach = work[dom]["flops"] / (v["total_ms"] * 1e-3) / 1e12
                 line["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
@@ -465,7 +527,10 @@ def run_ours(args):
         line["step_roofline"] = {"decode_step_floor_us": round(step_roof_ms * 1000, 1), "ar_floor_ms": round(step_roof_ms * S, 2),
                                  "vq_floor_ms": round(vq_roof_ms, 2), "measured_ms_per_step": round(ms / args.steps, 2),
                                  "frac_of_floor": round((step_roof_ms * S + vq_roof_ms) / (ms / args.steps), 4),
-                                 "traced_ar_kernel_ms": round(total_ms - total_vq, 2), "traced_vq_kernel_ms": round(total_vq, 2)}
+                                 "traced_ar_kernel_ms": round(total_ms - total_vq, 2), "traced_vq_kernel_ms": round(total_vq, 2),
+                                 "traced_step_wall_ms": round(traced_wall_ms, 2),
+                                 "note": "traced_* come from the single-chain, PDL-off trace step (sum of isolated kernel durations <= its wall time); "
+                                         "measured_ms_per_step is the shipped configuration"}
 
     # ---------------- batch-1 per-token latency (BASELINE.json metric, second half), rank 0
     if rank == 0 and not args.no_latency:
@@ -485,6 +550,54 @@ def run_ours(args):
         floor_us = 1e6 * alg1["step_bytes"] / (peaks()["hbm_gbs"] * 1e9)
         line["latency_b1"] = {"us_per_token": round(us_tok, 2), "hbm_floor_us": round(floor_us, 2), "frac_of_hbm_roofline": round(floor_us / us_tok, 4),
                               "rows": 2, "note": "generate() of 1 image incl. prefill and sampling, / tokens"}
+
+    # ---------------- north_star's per-GPU operating point (B=256 over 8 GPUs -> 32 images per GPU), our arm, rank 0
+    if rank == 0 and world == 1 and not args.no_operating_points and B != 32:
+        b2 = 32
+        gpt._workspace, gpt._ws_shape = None, (0, 0)          # a workspace sized for R = 64 rows (the chain split keys on it)
+        lab2 = torch.randint(0, 1000, (b2,), device=dev)
+        for _ in range(2):
+            pipe.submit(lab2, g)
+        pipe.wait()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n2 = 4
+        ev0.record()
+        for _ in range(n2):
+            pipe.submit(lab2, g)
+        pipe.wait()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms2 = ev0.elapsed_time(ev1) / n2
+        line["operating_points"] = {"batch32": {"images_per_s": b2 * 1000.0 / ms2, "ms_per_step": ms2, "rows": 2 * b2,
+                                                "note": "north_star headline shape: GPT-L 256-token c2i at B=256 over 8 GPUs = 32 images per GPU"}}
+        gpt._workspace, gpt._ws_shape = None, (0, 0)
+
+    # ---------------- reference PyTorch-GPU path on this same GPU (the number north_star asks us to beat), rank 0, N=1
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "gpu-reference", "--gpt-model", args.gpt_model,
+                                "--image-size", str(args.image_size), "--cfg-scale", str(args.cfg_scale), "--top-k", str(args.top_k),
+                                "--gpu-reference-batches", ",".join([str(B)] + [b for b in args.gpu_reference_batches.split(",") if b and int(b) != B][:1])],
+                               capture_output=True, text=True, timeout=900, env={**os.environ, "CUDA_VISIBLE_DEVICES": str(local)})
+            ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            line["gpu_reference"] = ref["gpu_reference"]
+            ours = {str(B): value / world}
+            if "operating_points" in line:
+                ours["32"] = line["operating_points"]["batch32"]["images_per_s"]
+            for b, res in line["gpu_reference"]["batches"].items():
+                best = max((res.get(k, {}).get("images_per_s") or 0.0) for k in ("eager", "compiled"))
+                if b in ours and best > 0:
+                    res["ours_images_per_s"] = ours[b]
+                    res["ours_over_best_reference"] = ours[b] / best
+        except Exception as ex:   # never silently drop the leg
+            tail = ""
+            try:
+                tail = r.stderr[-300:]
+            except Exception:
+                pass
+            line["gpu_reference"] = {"error": f"{type(ex).__name__}: {str(ex)[-200:]} {tail}"}
+        log("gpu reference leg done")
 
     # ---------------- CPU baseline leg (rank 0, N=1 only): bounded sample of the same workload on the host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -527,6 +640,9 @@ def emit(line: dict):
 def main():
     args = parse()
     quiet_stdout()
+    if args.impl == "gpu-reference":
+        run_gpu_reference(args)
+        return
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         run_reference(args, rank)

@@ -53,6 +53,7 @@ struct AttnTmaArgs {
     const float* partial; int ksplit;
     const float* freqs;
     bf16* kcache; bf16* vcache;
+    unsigned long long kvhint;   // L2 eviction hint of the K/V stream (0: default policy)
 };
 
 // FUSED = true: the kernel also IS the QKV epilogue of gpt.py:214-230 for its (row, head): it reduces the split-K
@@ -110,8 +111,8 @@ __global__ void __launch_bounds__(kWarps * 32 * (NST > 2 ? NST : 1), NST > 2 ? 1
             mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
-                load_2d(kt + sub * SUB_BYTES, &kmap, &full_bar[s], sub * 64, row);
-                load_2d(vt + sub * SUB_BYTES, &vmap, &full_bar[s], sub * 64, row);
+                load_2d_hint(kt + sub * SUB_BYTES, &kmap, &full_bar[s], sub * 64, row, a.kvhint);
+                load_2d_hint(vt + sub * SUB_BYTES, &vmap, &full_bar[s], sub * 64, row, a.kvhint);
             }
         } else {
             // tail chunk: 16-row boxes (one per warp's key group) so at most 15 rows beyond the context are read;
@@ -121,8 +122,8 @@ __global__ void __launch_bounds__(kWarps * 32 * (NST > 2 ? NST : 1), NST > 2 ? 1
             for (int i = 0; i < n16; ++i) {
 #pragma unroll
                 for (int sub = 0; sub < NSUB; ++sub) {
-                    load_2d(kt + sub * SUB_BYTES + i * 2048, &kmap16, &full_bar[s], sub * 64, row + 16 * i);
-                    load_2d(vt + sub * SUB_BYTES + i * 2048, &vmap16, &full_bar[s], sub * 64, row + 16 * i);
+                    load_2d_hint(kt + sub * SUB_BYTES + i * 2048, &kmap16, &full_bar[s], sub * 64, row + 16 * i, a.kvhint);
+                    load_2d_hint(vt + sub * SUB_BYTES + i * 2048, &vmap16, &full_bar[s], sub * 64, row + 16 * i, a.kvhint);
                 }
             }
         }
@@ -525,6 +526,7 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     t.emb_mask = a.emb_mask; t.B = a.B; t.Tc = a.Tc; t.scale = a.scale;
     t.partial = a.qkv_partial; t.ksplit = a.qkv_ksplit; t.freqs = a.freqs;
     t.kcache = (bf16*)const_cast<void*>(a.kcache); t.vcache = (bf16*)const_cast<void*>(a.vcache);
+    t.kvhint = (lg_env_flag("LG_L2_HINT", 0) & 1) ? tma::kL2EvictFirst : 0ull;
     const CUtensorMap& km = *reinterpret_cast<const CUtensorMap*>(a.kmap);
     const CUtensorMap& vm = *reinterpret_cast<const CUtensorMap*>(a.vmap);
     const CUtensorMap& km16 = *reinterpret_cast<const CUtensorMap*>(a.kmap16);

@@ -21,9 +21,11 @@ extern std::atomic<uint64_t> g_lg_launches;
 #define LG_CUDA_OK(expr)                                                                         \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \
-        if (_e != cudaSuccess)                                                                   \
+        if (_e != cudaSuccess) {                                                                 \
+            (void)cudaGetLastError(); /* do not leave it behind for the next launch check */     \
             return lg_fail("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,                 \
                            cudaGetErrorString(_e));                                              \
+        }                                                                                        \
     } while (0)
 
 // LG_DEBUG_SYNC=1 synchronises after every launch and logs the launch site (hang / fault localisation).

@@ -143,6 +143,9 @@ struct lg_engine {
     Workspace full, sub[kMaxChains];      // sub[g]: rows/n_sub each, carved INSIDE the regions of `full` (multi-chain decode)
     int n_sub = 0;                        // 0: no split available
     bool use_graph = true;
+    PdLayerW* d_layers = nullptr;         // device copy of the per-layer weight pointers (persistent small-row decode kernel)
+    const int32_t* pd_tokens = nullptr;   // set by the caller of forward() when the step's token ids are in device memory and the
+                                          // embedding lookup has NOT been launched (the persistent kernel gathers the rows itself)
     bool ws_needs_zero = false;           // KV cache + counters of `full` still have to be zero-filled (done on the caller's stream)
     cudaStream_t works[kMaxChains] = {nullptr, nullptr, nullptr, nullptr};   // engine-owned streams (one per chain)
     cudaEvent_t ev_fork = nullptr, ev_joins[kMaxChains] = {nullptr, nullptr, nullptr, nullptr};
@@ -152,6 +155,13 @@ struct lg_engine {
             if (ev_joins[i]) cudaEventDestroy(ev_joins[i]);
         }
         if (ev_fork) cudaEventDestroy(ev_fork);
+        if (d_layers) cudaFree(d_layers);
+    }
+    // R <= 8 decode steps can run as ONE persistent cooperative kernel per token (decode_persist.cu)
+    bool persist_usable(int R) const {
+        return lg_env_flag("LG_PERSIST", 0) && d_layers && cfg.dtype == LG_DTYPE_BF16 && ws.have_maps &&
+               decode_persist_supported(R, cfg.dim, cfg.ffn_dim, cfg.vocab_size, cfg.n_head, hd, cfg.dtype) &&
+               decode_persist_part_floats(R, cfg.n_head, hd) <= ws.partial_floats;
     }
 
     size_t carve(Workspace& o, char* base, int rows, int max_seq) const;
@@ -199,6 +209,7 @@ size_t lg_engine::carve(Workspace& o, char* base, int rows, int max_seq) const {
         if (cfg.model_type == LG_MODEL_T2I) pf = std::max(pf, gemm_partial_floats(M, D, cfg.caption_dim, cfg.dtype));
     }
     pf = std::max(pf, gemm_partial_floats(rows, V, D, cfg.dtype));
+    if (cfg.dtype == LG_DTYPE_BF16) pf = std::max(pf, (size_t)std::min(rows, 8) * H * 8 * (hd + 2));   // decode_persist.cu partials
     o.partial_floats = pf;
     o.partial = (float*)take(pf * sizeof(float));
     o.logits = (float*)take((size_t)rows * V * sizeof(float));
@@ -243,6 +254,21 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         }
         return aa;
     };
+    // ---- R <= 8 decode step as ONE persistent cooperative kernel (decode_persist.cu): the caller passed the token ids
+    if (Tq == 1 && M <= 8 && pd_tokens) {
+        const int32_t* toks = pd_tokens;
+        pd_tokens = nullptr;
+        PdLaunch p{};
+        p.L = L; p.D = D; p.F = F; p.V = V; p.H = H; p.hd = hd; p.R = M; p.B = B; p.Tc = cfg.cls_token_num; p.maxS = ws.max_seq;
+        p.eps = cfg.norm_eps; p.scale = 1.0f / sqrtf((float)hd);
+        p.layers = d_layers; p.final_norm = final_norm; p.output = output; p.tok_emb = tok_emb; p.freqs = freqs;
+        p.kcache = ws.kcache; p.vcache = ws.vcache; p.layer_elems = ws.layer_cache_bytes / esz;
+        p.h = ws.h; p.q = ws.q; p.ff = ws.ff; p.part = ws.partial; p.part_floats = ws.partial_floats; p.logits = logits_out;
+        p.tokens = toks; p.pos_dev = pos.dev; p.pos_value = pos.value; p.emb_mask = emb_mask;
+        p.bar = (unsigned int*)(ws.counters + 96);
+        LG_PROF(PC_PERSIST, st, launch_decode_persist(p, st));
+        return 0;
+    }
     // ---- R <= 8 decode step (batch-1 latency path, gemv_small.cu): 5 dependent kernels per layer, no slabs
     if (Tq == 1 && M <= 8 && lg_env_flag("LG_SMALL_R", 1) && lg_env_flag("LG_FUSE_QKV", 1) && attn_tma_enabled() &&
         attn_tma_supported(attn_args(0)) && gemv_small_supported(M, 3 * D, D, dt, false) && gemv_small_supported(M, D, D, dt, false) &&
@@ -454,6 +480,17 @@ int lg_engine_finalize(lg_engine* e) {
     const void* fr = nullptr;
     LG_TRY(need(e, "freqs_cis", LG_DTYPE_F32, {c.cls_token_num + c.block_size, e->hd / 2, 2}, &fr));
     e->freqs = (const float*)fr;
+    if (dt == LG_DTYPE_BF16) {
+        DeviceGuard guard(e->device);
+        std::vector<PdLayerW> hl(c.n_layer);
+        for (int l = 0; l < c.n_layer; ++l) {
+            const Layer& ly = e->layers[l];
+            hl[l] = PdLayerW{(const bf16*)ly.wqkv, (const bf16*)ly.wo, (const bf16*)ly.w1, (const bf16*)ly.w3, (const bf16*)ly.w2,
+                             (const bf16*)ly.attn_norm, (const bf16*)ly.ffn_norm};
+        }
+        if (!e->d_layers) LG_CUDA_OK(cudaMalloc(&e->d_layers, sizeof(PdLayerW) * c.n_layer));
+        LG_CUDA_OK(cudaMemcpy(e->d_layers, hl.data(), sizeof(PdLayerW) * c.n_layer, cudaMemcpyHostToDevice));
+    }
     e->finalized = true;
     return 0;
 }
@@ -578,7 +615,8 @@ int lg_decode_step(lg_engine* e, const int32_t* tokens, int B, int pos, int use_
     LG_TRY(check_ready(e, R, pos + 1));
     LG_TRY(e->zero_fill_if_needed(st));
     LG_REQUIRE(tokens && logits_out && B > 0 && pos >= 0, "lg_decode_step: bad argument");
-    LG_TRY(launch_embed(e->tok_emb, tokens, B, R, -1, e->cfg.dim, e->cfg.dtype, e->ws.h, st));
+    if (e->persist_usable(R)) e->pd_tokens = tokens;
+    else LG_TRY(launch_embed(e->tok_emb, tokens, B, R, -1, e->cfg.dim, e->cfg.dtype, e->ws.h, st));
     PosArg p{nullptr, pos};
     LG_TRY(e->forward(R, 1, p, nullptr, B, logits_out, false, st));
     if (e->cfg.dtype == LG_DTYPE_BF16) LG_TRY(round_logits_inplace(logits_out, (size_t)R * e->cfg.vocab_size, st));
@@ -686,7 +724,8 @@ static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, 
         e->ws = k.w;
         int* d_pos = k.w.counters;
         int* d_step = k.w.counters + 1;
-        LG_PROF(PC_EMBED_MISC, k.st, launch_embed(e->tok_emb, k.w.tokens, k.B, k.R, -1, c.dim, c.dtype, k.w.h, k.st));
+        if (e->persist_usable(k.R)) e->pd_tokens = k.w.tokens;
+        else LG_PROF(PC_EMBED_MISC, k.st, launch_embed(e->tok_emb, k.w.tokens, k.B, k.R, -1, c.dim, c.dtype, k.w.h, k.st));
         LG_TRY(e->forward(k.R, 1, PosArg{d_pos, 0}, k.emb_mask, k.B, k.w.logits, false, k.st));
         LG_PROF(PC_SAMPLE, k.st, launch_sample(k.sa, k.st));
         LG_PROF(PC_EMBED_MISC, k.st, launch_advance(d_pos, d_step, k.st));
@@ -791,7 +830,7 @@ int lg_profile_read(int cls, double* total_ms, uint64_t* launches) {
 const char* lg_profile_class_name(int cls) {
     static const char* names[PC_COUNT] = {"gemm_qkv", "qkv_rope_kvwrite", "attention", "gemm_wo", "residual_rmsnorm",
                                           "gemm_w13", "silu_mul", "gemm_w2", "gemm_head", "sample", "embed_misc",
-                                          "vq_conv_gemm", "vq_gn_stats", "vq_gn_apply", "vq_attn", "vq_misc"};
+                                          "vq_conv_gemm", "vq_gn_stats", "vq_gn_apply", "vq_attn", "vq_misc", "persistent_decode"};
     return (cls >= 0 && cls < PC_COUNT) ? names[cls] : nullptr;
 }
 

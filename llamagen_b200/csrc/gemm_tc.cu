@@ -44,6 +44,7 @@ struct TcArgs {
     const char* pf0; unsigned long long pfb0;   // next GEMM's weights to pull into L2 (see GemmNext)
     const char* pf1; unsigned long long pfb1;
     unsigned long long* trace;   // debug: [cta][8] %globaltimer stamps of the pipeline phases (nullable)
+    unsigned long long whint;    // L2 eviction hint of the weight tiles (0: default policy)
 };
 
 // Epilogue of the CLUSTER variant (gemm_tc_cluster_kernel); the default kernel never sees this struct.
@@ -150,7 +151,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
             const int npre = min(nkb, kStages);
             for (int i = 0; i < npre; ++i) {
                 mbar_expect_tx(&full_bar[i], tx);
-                load_2d(tiles + i * stage_bytes, wmap, &full_bar[i], (kb0 + i) * kBlockK, wrow);
+                load_2d_hint(tiles + i * stage_bytes, wmap, &full_bar[i], (kb0 + i) * kBlockK, wrow, a.whint);
             }
             lg_pdl_wait();
             for (int i = 0; i < npre; ++i)
@@ -161,7 +162,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 mbar_expect_tx(&full_bar[s], tx);
                 uint8_t* sa = tiles + s * stage_bytes;
-                load_2d(sa, wmap, &full_bar[s], (kb0 + i) * kBlockK, wrow);
+                load_2d_hint(sa, wmap, &full_bar[s], (kb0 + i) * kBlockK, wrow, a.whint);
                 load_2d(sa + kATileBytes, &map_x, &full_bar[s], (kb0 + i) * kBlockK, 0);
             }
             // ask L2 for this CTA's share of the next GEMM's weights (static chain: qkv -> wo -> w1|w3 -> w2 -> next qkv)
@@ -534,6 +535,7 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
     // whole K range before the dependency wait: 3 -> 4 stages = 297.2 -> 294.9 ms/step (2 runs each), 5 no better.
     a.stages = std::min(a.stages, std::max(2, a.kblocks_per_split));   // never more stages than k-blocks
     a.trace = g_tc_trace;
+    a.whint = (lg_env_flag("LG_L2_HINT", 0) & 2) ? tma::kL2EvictLast : 0ull;
     const bool pf = next && lg_env_flag("LG_L2_PREFETCH", 1);
     a.pf0 = pf ? (const char*)next->p0 : nullptr; a.pfb0 = pf ? next->b0 : 0;
     a.pf1 = pf ? (const char*)next->p1 : nullptr; a.pfb1 = pf ? next->b1 : 0;
@@ -554,7 +556,11 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
     if ((fuse || lg_env_flag("LG_TC_CLUSTER", 0) == 1) && fits) {
         static DevOnce cattr;
         if (lg_first_on_device(cattr)) {
-            LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            // the kernel also has a few bytes of STATIC shared memory (s_last): the opt-in limit covers static + dynamic
+            cudaFuncAttributes fa;
+            LG_CUDA_OK(cudaFuncGetAttributes(&fa, gemm_tc_cluster_kernel));
+            LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            227 * 1024 - (int)((fa.sharedSizeBytes + 127) / 128 * 128)));
             LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         }
         cudaLaunchConfig_t cfg = {};

@@ -143,6 +143,25 @@ struct GemvSmall {
 bool gemv_small_supported(int R, int N, int K, int dtype, bool paired);
 int launch_gemv_small(const GemvSmall& g, cudaStream_t st);
 
+// decode_persist.cu — one cooperative launch per token for R <= 8 rows: every layer + the head, phases separated by grid
+// barriers, weights and old K/V rows streamed through a shared-memory ring by a producer warp that never waits on activations.
+struct PdLayerW { const bf16 *wqkv, *wo, *w1, *w3, *w2, *attn_norm, *ffn_norm; };
+struct PdLaunch {
+    int L, D, F, V, H, hd, R, B, Tc, maxS;
+    float eps, scale;
+    const PdLayerW* layers;            // DEVICE array [L]
+    const void *final_norm, *output, *tok_emb;
+    const float* freqs;
+    void *kcache, *vcache; size_t layer_elems;     // layer 0 base, elements between layers
+    void *h, *q, *ff; float* part; size_t part_floats; float* logits;
+    const int32_t* tokens; const int* pos_dev; int pos_value;
+    const float* emb_mask;
+    unsigned int* bar;                 // 2 zero-initialised counters
+};
+bool decode_persist_supported(int R, int D, int F, int V, int H, int hd, int dtype);
+size_t decode_persist_part_floats(int R, int H, int hd);      // fp32 scratch the attention partials need
+int launch_decode_persist(const PdLaunch& p, cudaStream_t st);
+
 // *pos += 1; *step += 1  (device-side loop counters for graph replay)
 int launch_advance(int* pos, int* step, cudaStream_t st);
 int launch_set_counters(int* pos, int pos_v, int* step, int step_v, cudaStream_t st);
@@ -153,7 +172,7 @@ int launch_set_counters(int* pos, int pos_v, int* step, int step_v, cudaStream_t
 // ------------------------------------------------------------------------------------------------
 enum ProfClass {
     PC_GEMM_QKV = 0, PC_QKV_EPI, PC_ATTENTION, PC_GEMM_WO, PC_RESNORM, PC_GEMM_W13, PC_SILU, PC_GEMM_W2,
-    PC_GEMM_HEAD, PC_SAMPLE, PC_EMBED_MISC, PC_VQ_CONV, PC_VQ_GN_STATS, PC_VQ_GN_APPLY, PC_VQ_ATTN, PC_VQ_MISC,
+    PC_GEMM_HEAD, PC_SAMPLE, PC_EMBED_MISC, PC_VQ_CONV, PC_VQ_GN_STATS, PC_VQ_GN_APPLY, PC_VQ_ATTN, PC_VQ_MISC, PC_PERSIST,
     PC_COUNT
 };
 bool prof_enabled();

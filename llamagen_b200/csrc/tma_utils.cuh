@@ -52,6 +52,21 @@ __device__ __forceinline__ void load_2d(void* smem_dst, const CUtensorMap* map, 
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// L2 eviction-priority hints for bulk tensor loads (the encodings createpolicy.fractional.L2::evict_* produce with fraction 1.0):
+// KV-cache streams are read once per step (evict_first), weights are re-read by the second decode chain and by the next token
+// (evict_last). hint == 0 keeps the default policy.
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t hint) {
+    if (hint == 0) {
+        load_2d(smem_dst, map, bar, c0, c1);
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+            : "memory");
+    }
+}
 __device__ __forceinline__ void load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"

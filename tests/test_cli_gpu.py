@@ -122,3 +122,41 @@ def test_serve_llm_generate_matches_generate():
         llm.generate(prompt_token_ids=[[1], [2]], sampling_params=sp)        # cfg on but no null-class twins
     with pytest.raises(ValueError):
         LLM(gpt, cfg_scale=1.0).generate(prompt_token_ids=[[1, 2]])
+
+
+def test_t2i_feature_files_to_tokens_match_oracle(tmp_path):
+    """SURVEY §8 f-3, value check: T5 feature FILES (the fp32 [1, valid_len, dim] .npy layout of language/extract_t5_feature.py:103-108)
+    -> cond.load_t5_feature_files -> cond.prepare_condition (batched left-padding) -> generate() must give the greedy tokens
+    the ORACLE produces from the reference's own per-prompt front end (sample_t2i.py:92-106, restated inline below).
+    fp32 exact mode on the reference-made golden t2i model: token ids bit-exact, logits <= 1e-4."""
+    import torch
+    from llamagen_b200 import generate
+    from llamagen_b200.cond import load_t5_feature_files, prepare_condition
+    from oracle import GPTOracle
+    from util import build_gpt, load_golden
+    g = load_golden("gpt_t2i.pt")
+    T, C, S = g["cfg"]["cls_token_num"], g["cfg"]["caption_dim"], g["S"]
+    rng = np.random.default_rng(7)
+    lens = [5, 37, 120, 64]
+    paths = []
+    for i, n in enumerate(lens):
+        np.save(tmp_path / f"{i}.npy", rng.standard_normal((1, n, C)).astype(np.float32))
+        paths.append(str(tmp_path / f"{i}.npy"))
+    # --- reference front end (sample_t2i.py:89-106): right-padded features + mask as T5Embedder returns them, then the per-prompt loop
+    embs = torch.zeros(len(lens), T, C)
+    masks = torch.zeros(len(lens), T)
+    for i, n in enumerate(lens):
+        embs[i, :n] = torch.from_numpy(np.load(paths[i]))[0]
+        masks[i, :n] = 1
+    new_masks = torch.flip(masks, dims=[-1])
+    new_embs = torch.stack([torch.cat([e[int(m.sum().item()):], e[:int(m.sum().item())]]) for e, m in zip(embs, masks)])
+    ref_cond, ref_masks = new_embs * new_masks[:, :, None], new_masks
+    ref_t, ref_l = GPTOracle(g["state_dict"], g["cfg"]).generate(ref_cond, S, emb_masks=ref_masks, cfg_scale=4.0, sample_logits=False)
+    # --- product front end + engine
+    m = build_gpt(g["cfg"], g["state_dict"], torch.float32)
+    e2, m2 = load_t5_feature_files(paths, T, C)
+    cond, cmask = prepare_condition(e2.cuda(), m2.cuda(), left_padding=True)
+    assert torch.equal(cond.cpu(), ref_cond) and torch.equal(cmask.cpu(), ref_masks)
+    toks, logits = generate(m, cond, S, emb_masks=cmask, cfg_scale=4.0, sample_logits=False, return_logits=True)
+    assert (logits.cpu() - ref_l).abs().max().item() <= 1e-4
+    assert torch.equal(toks.cpu(), ref_t)

@@ -304,3 +304,55 @@ def test_experimental_fused_cluster_decode_path(B, monkeypatch):
     a = generate(m, cond.cuda(), 24, cfg_scale=4.0, top_k=100, seed=3)
     b = generate(m, cond.cuda(), 24, cfg_scale=4.0, top_k=100, seed=3)
     assert torch.equal(a, b)                      # the arrival counters only decide WHO normalises a row, never the value
+
+
+@pytest.mark.parametrize("model,B", [("GPT-B", 1), ("GPT-B", 4), ("GPT-L", 1)])
+def test_persistent_decode_kernel_vs_oracle(model, B, monkeypatch):
+    """LG_PERSIST=1: R <= 8 decode steps run as ONE cooperative persistent kernel per token (decode_persist.cu: grid barriers between
+    phases, weights + old K/V rows streamed through a shared-memory ring). Same oracle bound as every other bf16 path, and it must
+    agree with the 5-kernel small-row path (same rounding points, different fp32 summation order)."""
+    monkeypatch.setenv("LG_PERSIST", "1")
+    m = _registry_model(model, torch.bfloat16, 2, block_size=256, vocab_size=16384)
+    torch.manual_seed(30 + B)
+    cond = torch.randint(0, 1000, (B,))
+    _bf16_parity(m, cond, 12)
+    teacher = torch.randint(0, 16384, (B, 40), generator=torch.Generator().manual_seed(B), dtype=torch.int32)
+    _, pers = _gen(m, cond, 40, None, cfg_scale=4.0, teacher=teacher.clone())
+    monkeypatch.setenv("LG_PERSIST", "0")
+    _, small = _gen(m, cond, 40, None, cfg_scale=4.0, teacher=teacher.clone())
+    err = (pers - small).abs()
+    scale = small.std().item()
+    assert err.max().item() <= 0.08 * scale + 0.02, (err.max().item(), scale)
+    assert err.mean().item() <= 0.01 * scale + 0.002, (err.mean().item(), scale)
+    monkeypatch.setenv("LG_PERSIST", "1")
+    from llamagen_b200 import generate
+    a = generate(m, cond.cuda(), 32, cfg_scale=4.0, top_k=100, seed=3)
+    b = generate(m, cond.cuda(), 32, cfg_scale=4.0, top_k=100, seed=3)
+    assert torch.equal(a, b)                                   # no atomics on the data path: bit-reproducible
+
+
+@pytest.mark.parametrize("nsplit", ["0", "1", "3"])
+def test_persistent_decode_long_context_and_masks(nsplit, monkeypatch):
+    """Persistent kernel on a t2i model: masked 120-token condition prefix + a 300-token image (contexts to 420 keys). LG_PD_NSPLIT
+    forces 1 / 3 context slices per (row, head) so units span several 64-key ring tiles; 0 = the automatic split."""
+    from llamagen_b200.gpt import ModelArgs, Transformer
+    torch.manual_seed(8)
+    m = Transformer(ModelArgs(n_layer=3, n_head=4, dim=256, block_size=324, vocab_size=1024, cls_token_num=120, caption_dim=64,
+                              model_type="t2i"))
+    m.output.weight.data.normal_(std=0.02)
+    m = m.to(device="cuda", dtype=torch.bfloat16).eval()
+    B, S = 3, 300
+    em = torch.zeros(B, 120)
+    for b, n in enumerate((5, 61, 120)):
+        em[b, -n:] = 1
+    cond = (torch.randn(B, 120, 64) * em[:, :, None]).bfloat16()
+    teacher = torch.randint(0, 1024, (B, S), generator=torch.Generator().manual_seed(5), dtype=torch.int32)
+    monkeypatch.setenv("LG_PD_NSPLIT", nsplit)
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("LG_PERSIST", flag)
+        _, outs[flag] = _gen(m, cond, S, em, cfg_scale=3.0, teacher=teacher.clone())
+    err = (outs["1"] - outs["0"]).abs()
+    scale = outs["0"].std().item()
+    assert err.max().item() <= 0.2 * scale + 0.05, (err.max().item(), scale)
+    assert err.mean().item() <= 0.03 * scale + 0.005, (err.mean().item(), scale)
