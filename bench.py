@@ -42,6 +42,9 @@ def parse():
     p.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     p.add_argument("--cfg-scale", type=float, default=4.0)
     p.add_argument("--top-k", type=int, default=2000)
+    p.add_argument("--t2i", action="store_true",
+                   help="text-conditioned workload (BASELINE configs[4]): T=120 synthetic T5 features with ragged left-padded masks, "
+                        "caption-MLP prefill + S tokens; use with --gpt-model GPT-XL --image-size 512 --batch 8 --cfg-scale 7.5 --top-k 1000")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-roofline", action="store_true")
     p.add_argument("--no-gpu-reference", action="store_true",
@@ -340,7 +343,11 @@ def run_ours(args):
 
     # weights: rank 0 initialises, NCCL broadcasts once (north_star: "NCCL only for the initial weight broadcast")
     torch.manual_seed(args.seed)
-    gpt = GPT_models[args.gpt_model](block_size=S, vocab_size=16384)
+    T = 120 if args.t2i else 1
+    if args.t2i:
+        gpt = GPT_models[args.gpt_model](block_size=S, vocab_size=16384, cls_token_num=T, model_type="t2i")
+    else:
+        gpt = GPT_models[args.gpt_model](block_size=S, vocab_size=16384)
     gpt.output.weight.data.normal_(std=0.02)
     gpt = gpt.to(device=dev, dtype=torch.bfloat16).eval()
     vq = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).to(dev).eval()
@@ -353,19 +360,28 @@ def run_ours(args):
     use_pipe = os.environ.get("LG_BENCH_PIPELINE", "1") != "0"
     pipe = SamplePipeline(gpt, vq, 8, **kw)
 
+    emb_masks = None
+    if args.t2i:     # randn(B,120,2048) x left-padded mask with valid lengths randint(8,120)
+        from llamagen_b200.cond import prepare_condition, synthetic_features
+        feats, fmask = synthetic_features(B, T, 2048, args.seed + 17, dev, torch.bfloat16)
+        cond_t2i, emb_masks = prepare_condition(feats, fmask, left_padding=True)
+
     def step_resident(labels_dev):
         if use_pipe:       # VQ decode of this batch overlaps the AR sampling of the next one (decode stream)
-            return pipe.submit(labels_dev, g)
-        toks = generate(gpt, labels_dev, S, **kw)
+            return pipe.submit(labels_dev, g, emb_masks=emb_masks)
+        toks = generate(gpt, labels_dev, S, emb_masks=emb_masks, **kw)
         return vq.decode_code(toks, qz)
 
-    host_labels = torch.randint(0, 1000, (B,), dtype=torch.int64).pin_memory()
+    if args.t2i:
+        host_labels = cond_t2i.cpu().pin_memory()
+    else:
+        host_labels = torch.randint(0, 1000, (B,), dtype=torch.int64).pin_memory()
     host_pixels = torch.empty(B, args.image_size, args.image_size, 3, dtype=torch.uint8).pin_memory()
 
     def step_e2e():
         labels = host_labels.to(dev, non_blocking=True)                       # H2D every step
         if use_pipe:
-            return pipe.submit(labels, g, to_uint8_host=host_pixels)          # decode + uint8 + D2H on the decode stream
+            return pipe.submit(labels, g, to_uint8_host=host_pixels, emb_masks=emb_masks)   # decode + uint8 + D2H on the decode stream
         img = step_resident(labels)
         u8 = torch.clamp(127.5 * img + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)   # sample_c2i_ddp.py:143
         host_pixels.copy_(u8, non_blocking=True)                              # D2H every step
@@ -392,7 +408,7 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    labels_dev = torch.randint(0, 1000, (B,), device=dev)
+    labels_dev = cond_t2i if args.t2i else torch.randint(0, 1000, (B,), device=dev)
     log(f"rank {rank}: models ready, warming up")
     for _ in range(max(args.warmup, 3)):
         t0 = time.perf_counter()
@@ -418,15 +434,28 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"LlamaGen {args.gpt_model} c2i {args.image_size}px ({g}x{g} tokens), cfg={args.cfg_scale}, top_k={args.top_k}, "
+            "config": {"workload": f"LlamaGen {args.gpt_model} {'t2i (T=120 synthetic T5 features, ragged masks)' if args.t2i else 'c2i'} {args.image_size}px ({g}x{g} tokens), cfg={args.cfg_scale}, top_k={args.top_k}, "
                                    f"batch={B} per GPU (R={R} rows), AR sampling + VQ-16 decode to fp32 pixels",
+                       "kv_cache_bytes": int(4 * model_dims(args.gpt_model)[0] * R * model_dims(args.gpt_model)[2] * ((T + S + 7) // 8 * 8)),
                        "global_batch": world * B, "parallelism": f"replica-dp{world}", "weights": "random-init, output head normal(0.02)",
                        "l2": "working set per step (0.65 GB weights + KV cache up to 3.3 GB + 1 GB activations) exceeds the 126 MB L2; no flush needed",
                        "weight_broadcast_bytes": bcast_bytes,
                        "pipeline": "VQ decode of batch i on a second stream overlaps the AR sampling of batch i+1; all of it inside the timed region" if use_pipe else "sequential"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_labels.numel() * 8),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_labels.numel() * host_labels.element_size()),
                     "d2h_bytes_per_step": int(host_pixels.numel()), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks}
+
+    if rank == 0:      # condition prefill alone (c2i: one position; t2i: caption MLP + 120 positions), CUDA events
+        for _ in range(2):
+            generate(gpt, labels_dev, 1, emb_masks=emb_masks, **kw)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(5):
+            generate(gpt, labels_dev, 1, emb_masks=emb_masks, **kw)
+        ev1.record()
+        torch.cuda.synchronize()
+        line["prefill_ms"] = round(ev0.elapsed_time(ev1) / 5, 3)
 
     # ---------------- roofline leg: device-side kernel durations (CUPTI via torch.profiler) of one extra step, rank 0
     if rank == 0 and not args.no_roofline:
@@ -478,7 +507,7 @@ def run_ours(args):
             timing_source = "cudaEvent pairs around eager launches (includes launch latency)"
         else:
             timing_source = "CUPTI kernel timestamps inside the CUDA-graph replay (torch.profiler)"
-        alg = algorithmic(args.gpt_model, R, S)
+        alg = algorithmic(args.gpt_model, R, S, T=T)
         L = model_dims(args.gpt_model)[0]
         # algorithmic work of one whole step (S tokens, B images) per kernel class
         work = {
@@ -534,25 +563,26 @@ def run_ours(args):
 
     # ---------------- batch-1 per-token latency (BASELINE.json metric, second half), rank 0
     if rank == 0 and not args.no_latency:
-        lab1 = torch.randint(0, 1000, (1,), device=dev)
+        lab1 = cond_t2i[:1].contiguous() if args.t2i else torch.randint(0, 1000, (1,), device=dev)
+        em1 = emb_masks[:1].contiguous() if args.t2i else None
         for _ in range(3):
-            generate(gpt, lab1, S, **kw)
+            generate(gpt, lab1, S, emb_masks=em1, **kw)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         ev0.record()
         reps = 5
         for _ in range(reps):
-            generate(gpt, lab1, S, **kw)
+            generate(gpt, lab1, S, emb_masks=em1, **kw)
         ev1.record()
         torch.cuda.synchronize()
         us_tok = 1000.0 * ev0.elapsed_time(ev1) / reps / S
-        alg1 = algorithmic(args.gpt_model, 2, S)
+        alg1 = algorithmic(args.gpt_model, 2, S, T=T)
         floor_us = 1e6 * alg1["step_bytes"] / (peaks()["hbm_gbs"] * 1e9)
         line["latency_b1"] = {"us_per_token": round(us_tok, 2), "hbm_floor_us": round(floor_us, 2), "frac_of_hbm_roofline": round(floor_us / us_tok, 4),
                               "rows": 2, "note": "generate() of 1 image incl. prefill and sampling, / tokens"}
 
     # ---------------- north_star's per-GPU operating point (B=256 over 8 GPUs -> 32 images per GPU), our arm, rank 0
-    if rank == 0 and world == 1 and not args.no_operating_points and B != 32:
+    if rank == 0 and world == 1 and not args.no_operating_points and B != 32 and not args.t2i:
         b2 = 32
         gpt._workspace, gpt._ws_shape = None, (0, 0)          # a workspace sized for R = 64 rows (the chain split keys on it)
         lab2 = torch.randint(0, 1000, (b2,), device=dev)
@@ -574,7 +604,7 @@ def run_ours(args):
         gpt._workspace, gpt._ws_shape = None, (0, 0)
 
     # ---------------- reference PyTorch-GPU path on this same GPU (the number north_star asks us to beat), rank 0, N=1
-    if rank == 0 and world == 1 and not args.no_gpu_reference:
+    if rank == 0 and world == 1 and not args.no_gpu_reference and not args.t2i:
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "gpu-reference", "--gpt-model", args.gpt_model,
                                 "--image-size", str(args.image_size), "--cfg-scale", str(args.cfg_scale), "--top-k", str(args.top_k),
@@ -600,7 +630,7 @@ def run_ours(args):
         log("gpu reference leg done")
 
     # ---------------- CPU baseline leg (rank 0, N=1 only): bounded sample of the same workload on the host cores
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.t2i:
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
                                 "--gpt-model", args.gpt_model, "--image-size", str(args.image_size), "--batch", str(B)],

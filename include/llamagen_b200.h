@@ -132,6 +132,11 @@ int  lg_vq_workspace_bytes(lg_vq* v, int B, int grid, size_t* bytes);
 /* decode_code (vq_model.py:52-55): codes dev int32 [B, grid*grid] -> out dev f32 NCHW [B,3,H,W]. */
 int  lg_vq_decode(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws, size_t ws_bytes,
                   float* out_nchw, void* stream);
+/* decode_code followed by the samplers' pixel finishing (sample_c2i_ddp.py:141-143 without the optional resize):
+ * clamp(127.5*x + 128, 0, 255) -> uint8, NHWC [B,H,W,3], written straight from conv_out's accumulator drain (no fp32 image in
+ * HBM). Needs the tcgen05 conv path (every registry VQ model); bytes equal lg_vq_decode + lg_pixels_to_u8. */
+int  lg_vq_decode_u8(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws, size_t ws_bytes,
+                     uint8_t* out_nhwc, void* stream);
 /* VectorQuantizer.forward index path (vq_model.py:215-233): z dev f32 NCHW [B, e_dim, g, g] -> idx int64 [B*g*g]. */
 int  lg_vq_argmin(lg_vq* v, const float* z_nchw, int B, int grid, int64_t* out_idx, void* stream);
 /* VQModel.encode (vq_model.py:41-45): Encoder.forward :100-124 (Downsample :389-397) -> quant_conv -> VectorQuantizer.forward

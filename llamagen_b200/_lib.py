@@ -63,6 +63,7 @@ SIGNATURES = {
     "lg_vq_finalize": (c_int, [c_void_p, c_void_p]),
     "lg_vq_workspace_bytes": (c_int, [c_void_p, c_int, c_int, POINTER(c_size_t)]),
     "lg_vq_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "lg_vq_decode_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "lg_vq_argmin": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lg_vq_encode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
                              c_void_p]),

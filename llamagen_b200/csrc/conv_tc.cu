@@ -41,6 +41,7 @@ struct ConvTcArgs {
     const bf16* residual;
     bf16* out_bf;
     float* out_nchw;
+    uint8_t* out_u8;     // conv_out with the samplers' pixel finishing in the drain: uint8 NHWC [B][H][W][3] (sample_c2i_ddp.py:141-143)
 };
 
 __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap amap,
@@ -151,6 +152,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (n + j < a.Cout ? a.bias[n + j] : 0.f);
             }
+            if (a.out_u8) {         // conv_out -> clamp(127.5*x + 128, 0, 255) -> uint8 NHWC, same two roundings as torch's mul then add
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n + j < a.Cout)
+                        a.out_u8[opix * a.Cout + n + j] = (uint8_t)fminf(fmaxf(__fadd_rn(__fmul_rn(127.5f, f[j]), 128.0f), 0.f), 255.f);
+                continue;
+            }
             if (a.out_nchw) {       // conv_out: fp32 NCHW, Cout = 3
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
@@ -225,7 +233,7 @@ bool conv_tc_supported(int Hin, int Win, int Cin, int Cout, int ksize, int up, b
 
 // weights: up == 0 or 2 (stride-2 Downsample) -> [Cout][k*k][Cin] bf16 ; up == 1 -> phase weights [4][Cout][4][Cin] bf16
 int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16* weights, const float* bias, int Cout,
-                   int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st) {
+                   int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st, uint8_t* out_u8) {
     ConvTcArgs a;
     a.B = B; a.Hin = Hin; a.Win = Win; a.Cin = Cin; a.Cout = Cout;
     const bool down = up == 2;
@@ -242,7 +250,7 @@ int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16*
     a.kchunks = Cin / kCk;
     a.tmem_cols = 32;
     while (a.tmem_cols < a.bn) a.tmem_cols *= 2;
-    a.bias = bias; a.residual = residual; a.out_bf = out_bf; a.out_nchw = out_nchw;
+    a.bias = bias; a.residual = residual; a.out_bf = out_bf; a.out_nchw = out_nchw; a.out_u8 = out_u8;
 
     CUtensorMap amap, wmap;
     LG_TRY(tma::make_map_nhwc(&amap, in, (uint64_t)B, (uint64_t)Hin, (uint64_t)Win, (uint64_t)Cin, (uint32_t)a.bh, (uint32_t)a.bw, kCk,

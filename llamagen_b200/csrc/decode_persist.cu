@@ -55,6 +55,7 @@ struct PdArgs {
     const float* emb_mask;       // [B][Tc] or null
     unsigned int* bar;           // [0] grid-barrier counter, [1] exit counter (both zero between launches)
     int xs_bytes;                // bytes of the activation stage
+    unsigned long long* trace;   // debug: %globaltimer stamps [2 CTAs][L + 1][16] (nullable), see tools/persist_probe.py
 };
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -188,6 +189,14 @@ __global__ void __launch_bounds__(kThreadsPd, 1) decode_small_persistent_kernel(
 
     // ======================================================================================== compute warps
     const int g = lane >> 2, t = lane & 3;
+    const int tcta = cta == 0 ? 0 : (cta == G - 1 ? 1 : -1);
+    auto stamp = [&](int l, int k) {
+        if (a.trace && tcta >= 0 && tid == 0) {
+            unsigned long long tm;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm));
+            a.trace[((size_t)tcta * (a.L + 1) + l) * 16 + k] = tm;
+        }
+    };
     uint32_t seq = 0;                      // same tile sequence as the producer
     unsigned int bar_target = 0;
     auto grid_barrier = [&]() {
@@ -312,7 +321,9 @@ __global__ void __launch_bounds__(kThreadsPd, 1) decode_small_persistent_kernel(
         // ------------------------------------------------------------------------------------------------ P1: QKV
         {
             const Gemm gm{ly.wqkv, nullptr, 3 * D, D, phase_rot(l, 0, G)};
+            stamp(l, 0);
             stage_rows([&](int r) { return h_row(l, r); }, D, ly.attn_norm);
+            stamp(l, 1);
             const int f0 = first_group(gm, cta, G);
             run_gemm(gm, [&](int m0, int nb) {
                 // thread -> (group slot, feature pair, row): RoPE needs the (2j, 2j+1) pair (gpt.py:420-430)
@@ -338,7 +349,9 @@ __global__ void __launch_bounds__(kThreadsPd, 1) decode_small_persistent_kernel(
                 }
             });
         }
+        stamp(l, 2);
         grid_barrier();
+        stamp(l, 3);
         // ------------------------------------------------------------------------------------------------ P2: attention
         {
             float* qs = misc;                       // [hd] query (fp32)
@@ -449,7 +462,9 @@ __global__ void __launch_bounds__(kThreadsPd, 1) decode_small_persistent_kernel(
                 cbar();
             }
         }
+        stamp(l, 4);
         grid_barrier();
+        stamp(l, 5);
         // ------------------------------------------------------------------------------------------------ P3: wo + residual
         {
             const Gemm gm{ly.wo, nullptr, D, D, phase_rot(l, 2, G)};
@@ -474,6 +489,7 @@ __global__ void __launch_bounds__(kThreadsPd, 1) decode_small_persistent_kernel(
                 }
                 cbar();
             }
+            stamp(l, 6);
             const int f0 = first_group(gm, cta, G);
             run_gemm(gm, [&](int m0, int nb) {
                 for (int i = tid; i < nb * 4 * 8; i += kCT) {
@@ -487,11 +503,14 @@ __global__ void __launch_bounds__(kThreadsPd, 1) decode_small_persistent_kernel(
                 }
             });
         }
+        stamp(l, 7);
         grid_barrier();
+        stamp(l, 8);
         // ------------------------------------------------------------------------------------------------ P4: w1 | w3 + SwiGLU
         {
             const Gemm gm{ly.w1, ly.w3, F, D, phase_rot(l, 3, G)};
             stage_rows([&](int r) { return (const bf16*)(a.h + (size_t)r * D); }, D, ly.ffn_norm);
+            stamp(l, 9);
             const int f0 = first_group(gm, cta, G);
             run_gemm(gm, [&](int m0, int nb) {
                 for (int i = tid; i < nb * 4 * 8; i += kCT) {
@@ -508,11 +527,14 @@ __global__ void __launch_bounds__(kThreadsPd, 1) decode_small_persistent_kernel(
                 }
             });
         }
+        stamp(l, 10);
         grid_barrier();
+        stamp(l, 11);
         // ------------------------------------------------------------------------------------------------ P5: w2 + residual
         {
             const Gemm gm{ly.w2, nullptr, D, F, phase_rot(l, 4, G)};
             stage_rows([&](int r) { return (const bf16*)(a.ff + (size_t)r * F); }, F, nullptr);
+            stamp(l, 12);
             const int f0 = first_group(gm, cta, G);
             run_gemm(gm, [&](int m0, int nb) {
                 for (int i = tid; i < nb * 4 * 8; i += kCT) {
@@ -525,12 +547,16 @@ __global__ void __launch_bounds__(kThreadsPd, 1) decode_small_persistent_kernel(
                 }
             });
         }
+        stamp(l, 13);
         grid_barrier();
+        stamp(l, 14);
     }
     // ---------------------------------------------------------------------------------------------------- PH: final norm + head
     {
         const Gemm gm{a.output, nullptr, a.V, D, phase_rot(a.L, 0, G)};
+        stamp(a.L, 0);
         stage_rows([&](int r) { return (const bf16*)(a.h + (size_t)r * D); }, D, a.final_norm);
+        stamp(a.L, 1);
         const int f0 = first_group(gm, cta, G);
         run_gemm(gm, [&](int m0, int nb) {
             for (int i = tid; i < nb * 4 * 8; i += kCT) {
@@ -541,6 +567,7 @@ __global__ void __launch_bounds__(kThreadsPd, 1) decode_small_persistent_kernel(
             }
         });
     }
+    stamp(a.L, 2);
     // leave both counters at zero for the next launch: the last CTA to get here resets them (every CTA has passed all barriers)
     if (tid == 0) {
         __threadfence();
@@ -563,6 +590,9 @@ bool decode_persist_supported(int R, int D, int F, int V, int H, int hd, int dty
     const size_t xs = (size_t)R * (std::max(D, F) * 2 + 16);
     return xs <= 96 * 1024;
 }
+
+static unsigned long long* g_pd_trace = nullptr;
+extern "C" void lg_debug_set_pd_trace(unsigned long long* dev_buf) { g_pd_trace = dev_buf; }
 
 static int pd_sm_count() {
     static int sms[32] = {0};
@@ -594,6 +624,7 @@ int launch_decode_persist(const PdLaunch& p, cudaStream_t st) {
     a.tokens = p.tokens; a.pos_dev = p.pos_dev; a.pos_value = p.pos_value; a.emb_mask = p.emb_mask; a.bar = p.bar;
     // attention split: as many (row, head, context-slice) units as there are CTAs, at most 8 slices
     a.nsplit = pd_nsplit(p.R, p.H);
+    a.trace = g_pd_trace;
     LG_REQUIRE((size_t)p.R * p.H * a.nsplit * (p.hd + 2) <= p.part_floats, "decode_persist: attention partial buffer too small");
     a.xs_bytes = (int)(((size_t)p.R * (std::max(p.D, p.F) * 2 + 16) + 127) / 128 * 128);
     const size_t fixed = 2 * kMaxSlots * sizeof(uint64_t) + (size_t)a.xs_bytes + (size_t)(kCW * kGB * 64 + 512) * sizeof(float);

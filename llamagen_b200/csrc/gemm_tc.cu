@@ -27,6 +27,7 @@ constexpr int kBlockK = 64;     // bf16 elements per k-block = 128 B = one swizz
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 256;   // 8 warps: TMA producer, MMA issuer, then ALL of them drain the accumulator
 constexpr int kATileBytes = kBlockN * kBlockK * 2;   // 16 KB
+constexpr int kMaxRowsPerCta = 256;                  // UMMA N <= 256 = TMEM columns of one accumulator
 
 using namespace tma;
 
@@ -35,7 +36,8 @@ using namespace umma;
 struct TcArgs {
     int M, N, K;          // activations rows, weight rows, reduction
     int n_split;          // weight rows [0, n_split) come from map_wa, the rest from map_wb
-    int rpad;             // M rounded up to 16 (UMMA N)
+    int rpad;             // rows of one row block rounded up to 16 (UMMA N); M > 256 is cut into gridDim.z blocks of rblk rows
+    int rblk;             // rows per row block (== M when gridDim.z == 1)
     int kblocks_per_split;
     int tmem_cols;        // power of two >= max(32, rpad)
     int stages;           // smem ring depth (<= kMaxStages), sized to fit 227 KB
@@ -117,6 +119,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
     // paired form (CLUSTER, epi 2): blockIdx.x = 2*j + which; which 0 -> w1 tile j (rows [0, N/2)), which 1 -> w3 tile j
     const int n0 = tile_n0<CLUSTER>(a, fz);
     const int ks = blockIdx.y;
+    const int row0 = (int)blockIdx.z * a.rblk;               // first activation row of this CTA's row block (t2i prefill: M = R*120)
+    const int Mb = min(a.rblk, a.M - row0);                  // valid rows in the block
     if (threadIdx.x == 0) TC_TRACE(0);
     const int total_kb = (a.K + kBlockK - 1) / kBlockK;
     const int kb0 = ks * a.kblocks_per_split;
@@ -155,7 +159,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
             }
             lg_pdl_wait();
             for (int i = 0; i < npre; ++i)
-                load_2d(tiles + i * stage_bytes + kATileBytes, &map_x, &full_bar[i], (kb0 + i) * kBlockK, 0);
+                load_2d(tiles + i * stage_bytes + kATileBytes, &map_x, &full_bar[i], (kb0 + i) * kBlockK, row0);
             for (int i = npre; i < nkb; ++i) {
                 const int s = i % kStages;
                 const uint32_t ph = (uint32_t)((i / kStages) & 1);
@@ -163,7 +167,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
                 mbar_expect_tx(&full_bar[s], tx);
                 uint8_t* sa = tiles + s * stage_bytes;
                 load_2d_hint(sa, wmap, &full_bar[s], (kb0 + i) * kBlockK, wrow, a.whint);
-                load_2d(sa + kATileBytes, &map_x, &full_bar[s], (kb0 + i) * kBlockK, 0);
+                load_2d(sa + kATileBytes, &map_x, &full_bar[s], (kb0 + i) * kBlockK, row0);
             }
             // ask L2 for this CTA's share of the next GEMM's weights (static chain: qkv -> wo -> w1|w3 -> w2 -> next qkv)
             {
@@ -349,7 +353,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
                 }
             }
         } else {
-        float* out = a.partial + (size_t)ks * a.M * a.N;
+        float* out = a.partial + (size_t)ks * a.M * a.N + (size_t)row0 * a.N;
         if (nkb > 0) {
             mbar_wait(tmem_full_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -360,20 +364,20 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
                 uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 if (n < a.N) {
-                    if (c0 + 16 <= a.M) {
+                    if (c0 + 16 <= Mb) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) { *p = __uint_as_float(v[j]); p += stride; }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            if (c0 + j < a.M) *p = __uint_as_float(v[j]);
+                            if (c0 + j < Mb) *p = __uint_as_float(v[j]);
                             p += stride;
                         }
                     }
                 }
             }
         } else if (n < a.N) {
-            for (int r = c_begin; r < min(c_end, a.M); ++r) out[(size_t)r * a.N + n] = 0.f;
+            for (int r = c_begin; r < min(c_end, Mb); ++r) out[(size_t)r * a.N + n] = 0.f;
         }
         }
     } else {
@@ -484,15 +488,15 @@ extern "C" void lg_debug_set_tc_trace(unsigned long long* dev_buf) { g_tc_trace 
 // Plan: number of k-slices so that (N/128) * ksplit is ~104 CTAs (measured best on B200 for the decode shapes:
 // 148 -> 350 ms/step, 112 -> 341, 96 -> 340, 72 -> 352; fewer, fatter slices halve the fp32 slab traffic), >= 2 k-blocks per slice.
 int gemm_tc_ksplit(int M, int N, int K) {
-    (void)M;
-    const int tiles = cdiv(N, kBlockN), kb = cdiv(K, kBlockK);
+    // row blocks (M > 256: t2i prefill) already multiply the CTA count
+    const int tiles = cdiv(N, kBlockN) * cdiv(M, kMaxRowsPerCta), kb = cdiv(K, kBlockK);
     int ks = std::max(1, lg_env_flag("LG_TC_CTAS", 104) / std::max(tiles, 1));
     ks = std::min(ks, std::max(1, kb / 2));
     return std::min(ks, 16);
 }
 
 bool gemm_tc_supported(int M, int N, int K, int dtype) {
-    return dtype == LG_DTYPE_BF16 && M >= 1 && M <= 256 && K % 8 == 0 && N % 2 == 0;
+    return dtype == LG_DTYPE_BF16 && M >= 1 && K % 8 == 0 && N % 2 == 0;
 }
 
 // fuse == nullptr: the shipped path (slabs, or the plain cluster reduction under LG_TC_CLUSTER=1).
@@ -507,7 +511,10 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
                "gemm_tc: operands must be 16-byte aligned");
     TcArgs a;
     a.M = M; a.N = N; a.K = K; a.n_split = n_split;
-    a.rpad = ((M + 15) / 16) * 16;
+    a.rblk = M <= kMaxRowsPerCta ? M : kMaxRowsPerCta;
+    const int zblocks = cdiv(M, a.rblk);
+    LG_REQUIRE(zblocks <= 65535 && (zblocks == 1 || !fuse), "gemm_tc: %d row blocks not launchable here", zblocks);
+    a.rpad = ((a.rblk + 15) / 16) * 16;
     const bool pair = fuse && fuse->epi == 2;
     int ks = gemm_tc_ksplit(M, N, K);
     if (pair) ks = std::min(ks, 8);                       // cluster = 2 tiles x ks CTAs <= 16
@@ -515,7 +522,7 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
     a.kblocks_per_split = cdiv(kb, ks);
     // rows-as-lanes (swap = 0, 64-byte vector stores per thread) was measured SLOWER than features-as-lanes on B200:
     // each warp store then touches 32 different 128-byte lines (drain 2.8-3.2 us vs 1.1 us), so it stays opt-in.
-    a.swap = (lg_env_flag("LG_TC_NOSWAP", 0) && M > 64 && M <= kBlockN) ? 0 : 1;
+    a.swap = (lg_env_flag("LG_TC_NOSWAP", 0) && M > 64 && M <= kBlockN && zblocks == 1) ? 0 : 1;
     a.tmem_cols = 32;
     while (a.tmem_cols < (a.swap ? a.rpad : kBlockN)) a.tmem_cols *= 2;
     a.partial = partial;
@@ -524,7 +531,7 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
     CUtensorMap mwa, mwb, mx;
     LG_TRY(tma::make_map_2d(&mwa, Wa, (uint64_t)std::min(n_split, N), (uint64_t)K, (uint64_t)K, kBlockN, kBlockK));
     LG_TRY(tma::make_map_2d(&mwb, Wb, (uint64_t)std::max(N - n_split, Wb == Wa ? N : 1), (uint64_t)K, (uint64_t)K, kBlockN, kBlockK));
-    LG_TRY(tma::make_map_2d(&mx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, (uint32_t)a.rpad, kBlockK));
+    LG_TRY(tma::make_map_2d(&mx, X, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, (uint32_t)a.rpad, kBlockK));   // rows >= M read as zero
 
     const int b_tile_bytes = a.rpad * kBlockK * 2;
     const int stage_bytes = kATileBytes + (a.swap ? ((b_tile_bytes + 1023) / 1024) * 1024 : kATileBytes);
@@ -546,11 +553,11 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
         LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     LG_REQUIRE(smem <= 227 * 1024, "gemm_tc: shared memory %zu too large", smem);
-    dim3 grid(cdiv(N, kBlockN), ks);
+    dim3 grid(cdiv(N, kBlockN), ks, zblocks);
     // Experimental (LG_TC_CLUSTER=1|2, off by default, not yet validated on hardware): on-chip split-K reduction over DSMEM,
     // see gemm_tc_cluster_kernel. Without a fused epilogue it falls back to slabs when the cluster cannot be scheduled or
     // the tile does not fit the ring; a fused epilogue has no fallback here (the engine probes before it picks that path).
-    const bool fits = a.swap && ks >= (fuse ? 1 : 2) && ks <= 16 && N % 4 == 0 &&
+    const bool fits = a.swap && zblocks == 1 && ks >= (fuse ? 1 : 2) && ks <= 16 && N % 4 == 0 &&
                       (size_t)a.stages * stage_bytes >= (size_t)a.rpad * kBlockN * sizeof(float) &&
                       (!fuse || fuse->epi == 0 || (N % kBlockN == 0 && (!pair || (n_split * 2 == N && n_split % kBlockN == 0))));
     if ((fuse || lg_env_flag("LG_TC_CLUSTER", 0) == 1) && fits) {

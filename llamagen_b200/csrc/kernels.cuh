@@ -116,7 +116,7 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st);
 bool conv_tc_supported(int Hin, int Win, int Cin, int Cout, int ksize, int up, bool nchw_out);
 int conv_tc_make_phase_weights(const float* w_f32, bf16* out, int cout, int cin, cudaStream_t st);
 int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16* weights, const float* bias, int Cout,
-                   int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st);
+                   int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st, uint8_t* out_u8 = nullptr);
 // gemm_tc.cu — tcgen05/TMEM/TMA weight-streaming GEMM (bf16, M <= 256)
 int gemm_tc_ksplit(int M, int N, int K);
 bool gemm_tc_supported(int M, int N, int K, int dtype);

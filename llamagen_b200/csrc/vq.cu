@@ -641,13 +641,14 @@ int chunk_images(const lg_vq* v, int B, int g) {
 // ---- layer launchers --------------------------------------------------------------------------------
 // up: 0 = same resolution, 1 = nearest-2x upsample folded in, 2 = Downsample (pad right/bottom, stride 2)
 int run_conv(const ConvW& cw, const bf16* in, int B, int Hin, int Win, int up, const bf16* residual, bf16* out_bf,
-             float* out_nchw, cudaStream_t st) {
-    if (lg_env_flag("LG_CONV_TC", 1) && conv_tc_supported(Hin, Win, cw.cin, cw.cout, cw.k, up, out_nchw != nullptr) &&
+             float* out_nchw, cudaStream_t st, uint8_t* out_u8 = nullptr) {
+    if (lg_env_flag("LG_CONV_TC", 1) && conv_tc_supported(Hin, Win, cw.cin, cw.cout, cw.k, up, out_nchw != nullptr || out_u8 != nullptr) &&
         (up != 1 || cw.w_phase)) {
         LG_PROF(PC_VQ_CONV, st, launch_conv_tc(in, B, Hin, Win, cw.cin, up == 1 ? cw.w_phase : cw.w, cw.bias, cw.cout, cw.k, up, residual,
-                                               out_bf, out_nchw, st));
+                                               out_bf, out_nchw, st, out_u8));
         return 0;
     }
+    LG_REQUIRE(!out_u8, "uint8 output needs the tcgen05 conv path (Cin %% 64 == 0, LG_CONV_TC=1)");
     const int Hout = up == 1 ? 2 * Hin : (up == 2 ? Hin / 2 : Hin), Wout = up == 1 ? 2 * Win : (up == 2 ? Win / 2 : Win);
     const int M = B * Hout * Wout, K = cw.k * cw.k * cw.cin;
     mma::ConvA al{in, Hin, Win, cw.cin, Hout, Wout, cw.k, up, M};
@@ -867,11 +868,12 @@ int lg_vq_workspace_bytes(lg_vq* v, int B, int grid, size_t* bytes) {
     return 0;
 }
 
-int lg_vq_decode(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws, size_t ws_bytes, float* out_nchw, void* stream) {
+static int vq_decode_impl(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws, size_t ws_bytes, float* out_nchw, uint8_t* out_u8,
+                          void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LG_REQUIRE(v && v->finalized, "vq engine not finalized");
     DeviceGuard guard(v->device);
-    LG_REQUIRE(codes && dev_ws && out_nchw && B > 0 && grid > 0, "lg_vq_decode: bad argument");
+    LG_REQUIRE(codes && dev_ws && (out_nchw || out_u8) && B > 0 && grid > 0, "lg_vq_decode: bad argument");
     LG_REQUIRE(((uintptr_t)dev_ws & 255) == 0, "workspace must be 256-byte aligned");
     const lg_vq_cfg& c = v->cfg;
     const int Bc = chunk_images(v, B, grid);
@@ -902,9 +904,18 @@ int lg_vq_decode(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws, 
             }
         }
         LG_TRY(run_gn(v->norm_out, w.X, w.T, bc, H * W, 1, w.gn, st));
-        LG_TRY(run_conv(v->conv_out, w.T, bc, H, W, 0, nullptr, nullptr, out_nchw + (size_t)b0 * out_per_img, st));
+        LG_TRY(run_conv(v->conv_out, w.T, bc, H, W, 0, nullptr, nullptr, out_nchw ? out_nchw + (size_t)b0 * out_per_img : nullptr, st,
+                        out_u8 ? out_u8 + (size_t)b0 * out_per_img : nullptr));
     }
     return 0;
+}
+
+int lg_vq_decode(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws, size_t ws_bytes, float* out_nchw, void* stream) {
+    return vq_decode_impl(v, codes, B, grid, dev_ws, ws_bytes, out_nchw, nullptr, stream);
+}
+
+int lg_vq_decode_u8(lg_vq* v, const int32_t* codes, int B, int grid, void* dev_ws, size_t ws_bytes, uint8_t* out_nhwc, void* stream) {
+    return vq_decode_impl(v, codes, B, grid, dev_ws, ws_bytes, nullptr, out_nhwc, stream);
 }
 
 int lg_vq_argmin(lg_vq* v, const float* z_nchw, int B, int grid, int64_t* out_idx, void* stream) {

@@ -25,7 +25,7 @@ class SamplePipeline:
 
     def submit(self, cond, grid: int, to_uint8_host=None, emb_masks=None):
         """Enqueue generate() on the current stream and decode_code() on the decode stream. Returns the pixel tensor
-        (fp32 NCHW); it is complete once `self.decode_stream` (or `wait()`) has been synchronised. When
+        (fp32 NCHW; uint8 NHWC when `to_uint8_host` has the decoder's own resolution); it is complete once `self.decode_stream` (or `wait()`) has been synchronised. When
         `to_uint8_host` (a pinned uint8 [B,H',W',3] tensor) is given, the pixel finishing of sample_c2i_ddp.py:141-143
         (bicubic resize to H' x W' when that differs from the decoder's output, clamp, uint8, NHWC — one kernel,
         postprocess.to_uint8_nhwc) and the device-to-host copy are enqueued behind the decode as well."""
@@ -36,10 +36,17 @@ class SamplePipeline:
         self.decode_stream.wait_event(ready)
         tokens.record_stream(self.decode_stream)
         with torch.cuda.stream(self.decode_stream):
-            pixels = self.vq.decode_code(tokens, [tokens.shape[0], self.embed_dim, grid, grid])
-            if to_uint8_host is not None:
-                u8 = to_uint8_nhwc(pixels, size=(to_uint8_host.shape[1], to_uint8_host.shape[2]))
-                to_uint8_host.copy_(u8, non_blocking=True)
+            shape = [tokens.shape[0], self.embed_dim, grid, grid]
+            up = 2 ** (len(self.vq.config.decoder_ch_mult) - 1)
+            if to_uint8_host is not None and tuple(to_uint8_host.shape[1:3]) == (grid * up, grid * up):
+                # no resize wanted: conv_out's drain writes the uint8 NHWC bytes directly, no fp32 image in HBM
+                pixels = self.vq.decode_code_uint8(tokens, shape)
+                to_uint8_host.copy_(pixels, non_blocking=True)
+            else:
+                pixels = self.vq.decode_code(tokens, shape)
+                if to_uint8_host is not None:
+                    u8 = to_uint8_nhwc(pixels, size=(to_uint8_host.shape[1], to_uint8_host.shape[2]))
+                    to_uint8_host.copy_(u8, non_blocking=True)
         self._last = pixels
         return pixels
 

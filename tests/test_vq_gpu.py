@@ -202,3 +202,20 @@ def test_pixels_bicubic_resize_matches_torch(src, dst):
     diff = (out.int() - ref.int()).abs()
     assert diff.max().item() <= 1
     assert (diff != 0).float().mean().item() < 5e-3
+
+
+@pytest.mark.parametrize("name,g", [("VQ-16", 16), ("VQ-8", 16)])
+def test_decode_code_uint8_equals_decode_then_finishing(name, g):
+    """the uint8/NHWC conversion inside conv_out's accumulator drain (lg_vq_decode_u8) must give the same BYTES as
+    decode_code followed by the reference's finishing `clamp(127.5*x+128, 0, 255).permute(0,2,3,1).to(uint8)`
+    (sample_c2i_ddp.py:141-143) applied to our own fp32 pixels — the arithmetic per pixel is identical."""
+    from llamagen_b200 import VQ_models
+    torch.manual_seed(3)
+    vq = VQ_models[name](codebook_size=16384, codebook_embed_dim=8).to("cuda").eval()
+    codes = torch.randint(0, 16384, (3, g * g), device="cuda")
+    shape = [3, 8, g, g]
+    pix = vq.decode_code(codes, shape)
+    want = torch.clamp(127.5 * pix + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+    got = vq.decode_code_uint8(codes, shape)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == tuple(want.shape)
+    assert torch.equal(got, want)
