@@ -111,7 +111,6 @@ struct Workspace {
     float *partial = nullptr, *logits = nullptr;
     int32_t* tokens = nullptr;
     int* counters = nullptr;  // [0] = pos, [1] = step (chain g of a split uses [2g], [2g+1])
-    unsigned int* tc_counters = nullptr;   // 16 arrival counters of the experimental fused cluster GEMM (zero between launches)
     size_t layer_cache_bytes = 0;
     size_t partial_floats = 0;
     alignas(64) unsigned char kmap[128];   // CUtensorMap over the K / V cache regions (bf16 only)
@@ -214,8 +213,7 @@ size_t lg_engine::carve(Workspace& o, char* base, int rows, int max_seq) const {
     o.partial = (float*)take(pf * sizeof(float));
     o.logits = (float*)take((size_t)rows * V * sizeof(float));
     o.tokens = (int32_t*)take((size_t)rows * sizeof(int32_t));
-    o.counters = (int*)take(128 * sizeof(int));   // [0, 8): pos/step per chain; [32 + 16g, 48 + 16g): tc_counters of chain g
-    o.tc_counters = o.counters ? (unsigned int*)(o.counters + 32) : nullptr;
+    o.counters = (int*)take(128 * sizeof(int));   // [0, 8): pos/step per chain; [96, 98): grid-barrier counters of decode_persist.cu
     o.rows = rows;
     o.max_seq = max_seq;
     return off;
@@ -292,33 +290,6 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         return 0;
     }
     LG_PROF(PC_EMBED_MISC, st, launch_rmsnorm(ws.h, layers[0].attn_norm, ws.xn, M, D, cfg.norm_eps, dt, st));
-    // ---- Experimental (LG_TC_CLUSTER=2, off by default, NOT yet validated on hardware): the batched decode step with the
-    // split-K reduction and every row epilogue inside the GEMMs (gemm_tc_cluster_kernel) — 5 dependent kernels per layer.
-    if (Tq == 1 && dt == LG_DTYPE_BF16 && lg_env_flag("LG_TC_CLUSTER", 0) == 2 && lg_env_flag("LG_FUSE_QKV", 1) && attn_tma_enabled() &&
-        attn_tma_supported(attn_args(0)) && ws.tc_counters && gemm_tc_cluster_ok(M, 3 * D, D, 0) && gemm_tc_cluster_ok(M, D, D, 1) &&
-        gemm_tc_cluster_ok(M, 2 * F, D, 2) && gemm_tc_cluster_ok(M, D, F, 1)) {
-        for (int l = 0; l < L; ++l) {
-            const Layer& ly = layers[l];
-            TcFuse fq{0, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr};
-            LG_PROF(PC_GEMM_QKV, st, gemm_tc_fused(ws.xn, D, ly.wqkv, nullptr, 0, M, 3 * D, D, ws.partial, fq, st));
-            AttnArgs aa = attn_args(l);
-            aa.qkv_partial = ws.partial; aa.qkv_ksplit = 1; aa.freqs = freqs;
-            LG_PROF(PC_ATTENTION, st, launch_attention(aa, st));
-            TcFuse fo{1, ws.h, ly.ffn_norm, ws.xn, cfg.norm_eps, ws.tc_counters, nullptr};
-            LG_PROF(PC_GEMM_WO, st, gemm_tc_fused(ws.attn, D, ly.wo, nullptr, 0, M, D, D, nullptr, fo, st));
-            TcFuse f13{2, nullptr, nullptr, nullptr, 0.f, nullptr, ws.ff};
-            LG_PROF(PC_GEMM_W13, st, gemm_tc_fused(ws.xn, D, ly.w1, ly.w3, F, M, 2 * F, D, nullptr, f13, st));
-            const void* next_norm = (l + 1 < L) ? layers[l + 1].attn_norm : final_norm;
-            TcFuse f2{1, ws.h, next_norm, ws.xn, cfg.norm_eps, ws.tc_counters, nullptr};
-            LG_PROF(PC_GEMM_W2, st, gemm_tc_fused(ws.ff, F, ly.w2, nullptr, 0, M, D, F, nullptr, f2, st));
-        }
-        prof_begin(PC_GEMM_HEAD, st);
-        const int direct = gemm(ws.xn, R, V, D, output, nullptr, 0, &ks, logits_out, st, nullptr);
-        prof_end(st);
-        if (direct < 0) return direct;
-        if (direct == 0) LG_TRY(launch_reduce_f32(ws.partial, ks, R, V, logits_out, st));
-        return 0;
-    }
     for (int l = 0; l < L; ++l) {
         const Layer& ly = layers[l];
         char* kc = ws.kcache + (size_t)l * ws.layer_cache_bytes;
@@ -562,7 +533,6 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
                 w.logits = tmp.logits + (size_t)g * hr * c.vocab_size;
                 w.tokens = tmp.tokens + (size_t)g * hr;
                 w.counters = tmp.counters + 2 * g;
-                w.tc_counters = (unsigned int*)(tmp.counters + 32 + 16 * g);
                 const long long total_rows = (long long)c.n_layer * hr * c.n_head * max_seq;
                 LG_TRY(attn_tma_make_map(w.kmap, w.kcache, total_rows, e->hd));
                 LG_TRY(attn_tma_make_map(w.vmap, w.vcache, total_rows, e->hd));

@@ -49,18 +49,6 @@ struct TcArgs {
     unsigned long long whint;    // L2 eviction hint of the weight tiles (0: default policy)
 };
 
-// Epilogue of the CLUSTER variant (gemm_tc_cluster_kernel); the default kernel never sees this struct.
-struct TcFuseArgs {
-    int epi;                     // 0: fp32 tile -> partial   1: residual add (+ the RMSNorm that follows)   2: SwiGLU gate of a w1 | w3 tile pair
-    bf16* h;                     // epi 1: residual stream [M][N], updated in place
-    const bf16* normw;           // epi 1: weight of the following RMSNorm (nullable: no xn)
-    bf16* xn;                    // epi 1: normalised rows [M][N], written by the LAST feature tile to finish a row range
-    float eps;
-    unsigned int* counters;      // epi 1: [gridDim.y] self-resetting arrival counters, one per row range
-    bf16* ff;                    // epi 2: gate output [M][N/2]
-};
-struct TcNoFuse {};
-
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -71,38 +59,8 @@ __device__ __forceinline__ unsigned long long gtime() {
         if (a.trace) a.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); \
     } while (0)
 
-// ---- thread-block-cluster helpers (CLUSTER variant: the k-slices of one feature tile reduce over distributed shared memory)
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_cta_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ float4 ld_peer_f4(uint32_t local_addr, uint32_t rank) {
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
-    float4 v;
-    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
-    return v;
-}
-
-// CLUSTER = false: every k-slice CTA writes its fp32 partial tile to its own slab [ks][M][N]; the consumer kernel sums the slabs.
-// CLUSTER = true (experimental, LG_TC_CLUSTER=1, not validated on hardware yet): the gridDim.y k-slice CTAs of a feature tile
-// are one thread-block cluster; each parks its partial tile in shared memory, and CTA q sums rows [q*M/ks, (q+1)*M/ks) over the
-// peers IN SLAB ORDER through DSMEM (bit-identical to the slab sum) and writes the finished fp32 tile once: out is [1][M][N].
-template <bool CLUSTER, class FuseT>
-__device__ __forceinline__ int tile_n0(const TcArgs& a, const FuseT& fz) {
-    if constexpr (CLUSTER) {
-        if (fz.epi == 2) return ((blockIdx.x & 1) ? a.N / 2 : 0) + (int)(blockIdx.x >> 1) * kBlockN;
-    }
-    return blockIdx.x * kBlockN;
-}
-
-template <bool CLUSTER, class FuseT>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CUtensorMap& map_wb, const CUtensorMap& map_x,
-                                             const TcArgs& a, const FuseT& fz) {
+                                             const TcArgs& a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // stage s: A tile at s*stage_bytes (1024-aligned), B tile right after
     const int b_tile_bytes = a.rpad * kBlockK * 2;
@@ -116,8 +74,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // paired form (CLUSTER, epi 2): blockIdx.x = 2*j + which; which 0 -> w1 tile j (rows [0, N/2)), which 1 -> w3 tile j
-    const int n0 = tile_n0<CLUSTER>(a, fz);
+    const int n0 = blockIdx.x * kBlockN;
     const int ks = blockIdx.y;
     const int row0 = (int)blockIdx.z * a.rblk;               // first activation row of this CTA's row block (t2i prefill: M = R*120)
     const int Mb = min(a.rblk, a.M - row0);                  // valid rows in the block
@@ -224,135 +181,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
         const int n = n0 + q * 32 + lane;
         const int cols_half = ((a.rpad / 16 + 1) / 2) * 16;
         const int c_begin = half * cols_half, c_end = min(a.rpad, c_begin + cols_half);
-        if constexpr (CLUSTER) {
-            // (1) TMEM -> this CTA's fp32 tile [rpad][128] in shared memory; the operand ring is idle once tmem_full_bar fired
-            float* ctile = reinterpret_cast<float*>(tiles);
-            if (nkb > 0) {
-                mbar_wait(tmem_full_bar, 0);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-                uint32_t v[16];
-                if (nkb > 0) {
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = 0u;
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) ctile[(c0 + j) * kBlockN + q * 32 + lane] = __uint_as_float(v[j]);
-            }
-            cluster_sync_all();
-            // (2) this CTA's share of the rows, summed over the k-slice peers in slab order, then the epilogue
-            const int pair = fz.epi == 2 ? 1 : 0;
-            const int nsl = (int)gridDim.y;                          // k-slices
-            const int nct = nsl << pair, rank = (int)cluster_cta_rank();   // cluster = (1 or 2 tiles) x k-slices, x fastest
-            const int rows_per = (a.M + nct - 1) / nct;
-            const int r_begin = rank * rows_per, r_end = min(a.M, r_begin + rows_per);
-            for (int idx = threadIdx.x; idx < (r_end - r_begin) * (kBlockN / 4); idx += kThreads) {
-                const int r = r_begin + idx / (kBlockN / 4), f = (idx % (kBlockN / 4)) * 4;
-                const uint32_t la = smem_u32(ctile + r * kBlockN + f);
-                float4 acc = ld_peer_f4(la, 0u);
-                for (int pr = 1; pr < nsl; ++pr) {
-                    const float4 t = ld_peer_f4(la, (uint32_t)(pr << pair));
-                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-                }
-                if (fz.epi == 0) {
-                    float* o = a.partial + (size_t)r * a.N + n0 + f;
-                    if (n0 + f + 3 < a.N) {
-                        *reinterpret_cast<float4*>(o) = acc;
-                    } else {
-                        const float t4[4] = {acc.x, acc.y, acc.z, acc.w};
-                        for (int j = 0; j < 4; ++j)
-                            if (n0 + f + j < a.N) o[j] = t4[j];
-                    }
-                } else if (fz.epi == 1) {
-                    // h = x + f(x) in bf16 tensors (gpt.py:255-256), same rounding as residual_norm_kernel
-                    bf16* hp = fz.h + (size_t)r * a.N + n0 + f;
-                    const uint2 hv = *reinterpret_cast<const uint2*>(hp);
-                    const float h0 = __uint_as_float(hv.x << 16), h1 = __uint_as_float(hv.x & 0xffff0000u);
-                    const float h2 = __uint_as_float(hv.y << 16), h3 = __uint_as_float(hv.y & 0xffff0000u);
-                    const __nv_bfloat162 lo = __floats2bfloat162_rn(h0 + __bfloat162float(__float2bfloat16_rn(acc.x)),
-                                                                    h1 + __bfloat162float(__float2bfloat16_rn(acc.y)));
-                    const __nv_bfloat162 hi = __floats2bfloat162_rn(h2 + __bfloat162float(__float2bfloat16_rn(acc.z)),
-                                                                    h3 + __bfloat162float(__float2bfloat16_rn(acc.w)));
-                    uint2 ov;
-                    ov.x = *reinterpret_cast<const uint32_t*>(&lo);
-                    ov.y = *reinterpret_cast<const uint32_t*>(&hi);
-                    *reinterpret_cast<uint2*>(hp) = ov;
-                } else {
-                    // paired form: acc is the w1 tile (ranks 0, 2, ...), the w3 tile sits at the odd ranks
-                    float4 bcc = ld_peer_f4(la, 1u);
-                    for (int pr = 1; pr < nsl; ++pr) {
-                        const float4 t = ld_peer_f4(la, (uint32_t)((pr << 1) | 1));
-                        bcc.x += t.x; bcc.y += t.y; bcc.z += t.z; bcc.w += t.w;
-                    }
-                    const float av[4] = {acc.x, acc.y, acc.z, acc.w}, bv[4] = {bcc.x, bcc.y, bcc.z, bcc.w};
-                    float o4[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {        // silu_mul_kernel's rounding points (gpt.py:167)
-                        const float ar = __bfloat162float(__float2bfloat16_rn(av[j])), br = __bfloat162float(__float2bfloat16_rn(bv[j]));
-                        const float sv = __bfloat162float(__float2bfloat16_rn(ar / (1.0f + expf(-ar))));
-                        o4[j] = sv * br;
-                    }
-                    const __nv_bfloat162 lo = __floats2bfloat162_rn(o4[0], o4[1]), hi = __floats2bfloat162_rn(o4[2], o4[3]);
-                    uint2 ov;
-                    ov.x = *reinterpret_cast<const uint32_t*>(&lo);
-                    ov.y = *reinterpret_cast<const uint32_t*>(&hi);
-                    *reinterpret_cast<uint2*>(fz.ff + (size_t)r * (a.N / 2) + (size_t)(blockIdx.x >> 1) * kBlockN + f) = ov;
-                }
-            }
-            cluster_sync_all();      // no CTA may retire while a peer still reads its tile
-            if (fz.epi == 1 && fz.normw) {
-                // The RMSNorm that follows needs whole rows. Every feature tile bumps the arrival counter of its row range
-                // after publishing its slice of h; the tile that arrives last normalises those rows (fixed summation order
-                // inside that CTA, so the result does not depend on which tile it is). The counter resets itself.
-                __shared__ unsigned int s_last;
-                __threadfence();
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    const unsigned int old = atomicAdd(&fz.counters[rank], 1u);
-                    s_last = old == gridDim.x - 1 ? 1u : 0u;
-                    if (s_last) fz.counters[rank] = 0u;
-                }
-                __syncthreads();
-                if (s_last) {
-                    __threadfence();
-                    const int pieces = a.N / 8;
-                    for (int r = r_begin + warp; r < r_end; r += kThreads / 32) {
-                        const uint4* hr = reinterpret_cast<const uint4*>(fz.h + (size_t)r * a.N);
-                        float ss = 0.f;
-                        for (int pc = lane; pc < pieces; pc += 32) {
-                            const uint4 v = __ldcg(hr + pc);
-                            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
-                                ss = fmaf(lo, lo, ss);
-                                ss = fmaf(hi, hi, ss);
-                            }
-                        }
-                        ss = warp_sum(ss);
-                        const float rinv = 1.0f / sqrtf(ss / (float)a.N + fz.eps);
-                        uint4* xr = reinterpret_cast<uint4*>(fz.xn + (size_t)r * a.N);
-                        for (int pc = lane; pc < pieces; pc += 32) {
-                            const uint4 v = __ldcg(hr + pc), nw = __ldg(reinterpret_cast<const uint4*>(fz.normw) + pc);
-                            const uint32_t w4[4] = {v.x, v.y, v.z, v.w}, n4[4] = {nw.x, nw.y, nw.z, nw.w};
-                            uint32_t o4[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {   // (x.float() * rsqrt(mean + eps)).type_as(x) * weight  (gpt.py:143-148)
-                                const float lo = __bfloat162float(__float2bfloat16_rn(__uint_as_float(w4[j] << 16) * rinv)) * __uint_as_float(n4[j] << 16);
-                                const float hi = __bfloat162float(__float2bfloat16_rn(__uint_as_float(w4[j] & 0xffff0000u) * rinv)) *
-                                                 __uint_as_float(n4[j] & 0xffff0000u);
-                                const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-                                o4[j] = *reinterpret_cast<const uint32_t*>(&pk);
-                            }
-                            xr[pc] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-                        }
-                    }
-                }
-            }
-        } else {
+        {
         float* out = a.partial + (size_t)ks * a.M * a.N + (size_t)row0 * a.N;
         if (nkb > 0) {
             mbar_wait(tmem_full_bar, 0);
@@ -420,14 +249,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_wa,
                                                               const __grid_constant__ CUtensorMap map_wb,
                                                               const __grid_constant__ CUtensorMap map_x, TcArgs a) {
-    gemm_tc_body<false>(map_wa, map_wb, map_x, a, TcNoFuse{});
-}
-
-// Experimental: thread-block cluster over the k-slices (x 2 tiles in the paired form), DSMEM reduction, fused epilogue.
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_wa,
-                                                                      const __grid_constant__ CUtensorMap map_wb,
-                                                                      const __grid_constant__ CUtensorMap map_x, TcArgs a, TcFuseArgs fz) {
-    gemm_tc_body<true>(map_wa, map_wb, map_x, a, fz);
+    gemm_tc_body(map_wa, map_wb, map_x, a);
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -499,11 +321,8 @@ bool gemm_tc_supported(int M, int N, int K, int dtype) {
     return dtype == LG_DTYPE_BF16 && M >= 1 && K % 8 == 0 && N % 2 == 0;
 }
 
-// fuse == nullptr: the shipped path (slabs, or the plain cluster reduction under LG_TC_CLUSTER=1).
-// fuse != nullptr: the cluster kernel with that epilogue is REQUIRED (error if it cannot be launched); probe = plan and
-// query only, nothing is launched (return 0: launchable, 1: not launchable).
 static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
-                          float* partial, int* ksplit_out, cudaStream_t st, const GemmNext* next, const TcFuseArgs* fuse, bool probe) {
+                          float* partial, int* ksplit_out, cudaStream_t st, const GemmNext* next) {
     LG_REQUIRE(gemm_tc_supported(M, N, K, LG_DTYPE_BF16), "gemm_tc: unsupported shape %d %d %d", M, N, K);
     if (Wb == nullptr) { Wb = Wa; n_split = N; }
     LG_REQUIRE(n_split % kBlockN == 0 || n_split == N, "gemm_tc: weight segment boundary %d must be a multiple of %d", n_split, kBlockN);
@@ -513,11 +332,9 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
     a.M = M; a.N = N; a.K = K; a.n_split = n_split;
     a.rblk = M <= kMaxRowsPerCta ? M : kMaxRowsPerCta;
     const int zblocks = cdiv(M, a.rblk);
-    LG_REQUIRE(zblocks <= 65535 && (zblocks == 1 || !fuse), "gemm_tc: %d row blocks not launchable here", zblocks);
+    LG_REQUIRE(zblocks <= 65535, "gemm_tc: %d row blocks not launchable", zblocks);
     a.rpad = ((a.rblk + 15) / 16) * 16;
-    const bool pair = fuse && fuse->epi == 2;
-    int ks = gemm_tc_ksplit(M, N, K);
-    if (pair) ks = std::min(ks, 8);                       // cluster = 2 tiles x ks CTAs <= 16
+    const int ks = gemm_tc_ksplit(M, N, K);
     const int kb = cdiv(K, kBlockK);
     a.kblocks_per_split = cdiv(kb, ks);
     // rows-as-lanes (swap = 0, 64-byte vector stores per thread) was measured SLOWER than features-as-lanes on B200:
@@ -554,44 +371,6 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
     }
     LG_REQUIRE(smem <= 227 * 1024, "gemm_tc: shared memory %zu too large", smem);
     dim3 grid(cdiv(N, kBlockN), ks, zblocks);
-    // Experimental (LG_TC_CLUSTER=1|2, off by default, not yet validated on hardware): on-chip split-K reduction over DSMEM,
-    // see gemm_tc_cluster_kernel. Without a fused epilogue it falls back to slabs when the cluster cannot be scheduled or
-    // the tile does not fit the ring; a fused epilogue has no fallback here (the engine probes before it picks that path).
-    const bool fits = a.swap && zblocks == 1 && ks >= (fuse ? 1 : 2) && ks <= 16 && N % 4 == 0 &&
-                      (size_t)a.stages * stage_bytes >= (size_t)a.rpad * kBlockN * sizeof(float) &&
-                      (!fuse || fuse->epi == 0 || (N % kBlockN == 0 && (!pair || (n_split * 2 == N && n_split % kBlockN == 0))));
-    if ((fuse || lg_env_flag("LG_TC_CLUSTER", 0) == 1) && fits) {
-        static DevOnce cattr;
-        if (lg_first_on_device(cattr)) {
-            // the kernel also has a few bytes of STATIC shared memory (s_last): the opt-in limit covers static + dynamic
-            cudaFuncAttributes fa;
-            LG_CUDA_OK(cudaFuncGetAttributes(&fa, gemm_tc_cluster_kernel));
-            LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            227 * 1024 - (int)((fa.sharedSizeBytes + 127) / 128 * 128)));
-            LG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute at[2];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = pair ? 2u : 1u; at[0].val.clusterDim.y = (unsigned)ks; at[0].val.clusterDim.z = 1;
-        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[1].val.programmaticStreamSerializationAllowed = lg_pdl_enabled() ? 1 : 0;
-        cfg.attrs = at; cfg.numAttrs = 2;
-        int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, gemm_tc_cluster_kernel, &cfg) == cudaSuccess && nclusters >= 1) {
-            if (probe) return 0;
-            if (ksplit_out) *ksplit_out = 1;
-            TcFuseArgs fz = {};
-            if (fuse) fz = *fuse;
-            LG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_cluster_kernel, mwa, mwb, mx, a, fz));
-            LG_LAUNCH_CHECK();
-            return 0;
-        }
-        (void)cudaGetLastError();
-    }
-    if (probe) return 1;
-    LG_REQUIRE(fuse == nullptr, "gemm_tc: the fused cluster epilogue %d cannot be launched for M=%d N=%d K=%d", fuse ? fuse->epi : 0, M, N, K);
     (void)lg_launch(gemm_tc_kernel, dim3(grid), dim3(kThreads), smem, st, mwa, mwb, mx, a);
     LG_LAUNCH_CHECK();
     return 0;
@@ -599,28 +378,5 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
 
 int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
                     float* partial, int* ksplit_out, cudaStream_t st, const GemmNext* next) {
-    return gemm_tc_launch(X, ldx, Wa, Wb, n_split, M, N, K, partial, ksplit_out, st, next, nullptr, false);
-}
-
-static TcFuseArgs to_args(const TcFuse& f) {
-    TcFuseArgs z = {};
-    z.epi = f.epi; z.h = (bf16*)f.h; z.normw = (const bf16*)f.normw; z.xn = (bf16*)f.xn; z.eps = f.eps; z.counters = f.counters;
-    z.ff = (bf16*)f.ff;
-    return z;
-}
-
-bool gemm_tc_cluster_ok(int M, int N, int K, int epi) {
-    if (!gemm_tc_supported(M, N, K, LG_DTYPE_BF16)) return false;
-    // the plan only needs shapes: a 16-byte aligned dummy stands in for the operands (nothing is dereferenced in probe mode)
-    static __align__(16) char dummy[16];
-    TcFuseArgs z = {};
-    z.epi = epi;
-    const int n_split = epi == 2 ? N / 2 : N;
-    return gemm_tc_launch(dummy, K, dummy, epi == 2 ? dummy : nullptr, n_split, M, N, K, nullptr, nullptr, nullptr, nullptr, &z, true) == 0;
-}
-
-int gemm_tc_fused(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K, float* partial,
-                  const TcFuse& f, cudaStream_t st, const GemmNext* next) {
-    const TcFuseArgs z = to_args(f);
-    return gemm_tc_launch(X, ldx, Wa, Wb, n_split, M, N, K, partial, nullptr, st, next, &z, false);
+    return gemm_tc_launch(X, ldx, Wa, Wb, n_split, M, N, K, partial, ksplit_out, st, next);
 }

@@ -122,14 +122,6 @@ int gemm_tc_ksplit(int M, int N, int K);
 bool gemm_tc_supported(int M, int N, int K, int dtype);
 int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
                     float* partial, int* ksplit_out, cudaStream_t st, const GemmNext* next = nullptr);
-// Experimental (LG_TC_CLUSTER=2, off by default, not yet validated on hardware): the k-slice CTAs of a feature tile form a
-// thread-block cluster, reduce over DSMEM in slab order and apply the epilogue themselves:
-//   epi 0: fp32 [M][N] -> partial      epi 1: h = bf(h + bf(acc)) in place, and xn = rmsnorm(h) * normw by the last tile of a row range
-//   epi 2: ff[M][N/2] = bf(silu(bf(a))) * bf(b) for the (Wa tile j, Wb tile j) pair
-struct TcFuse { int epi; void* h; const void* normw; void* xn; float eps; unsigned int* counters; void* ff; };
-bool gemm_tc_cluster_ok(int M, int N, int K, int epi);
-int gemm_tc_fused(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K, float* partial,
-                  const TcFuse& f, cudaStream_t st, const GemmNext* next = nullptr);
 
 // gemv_small.cu — decode GEMMs for R <= 8 rows: CTA-owned output columns (no split-K), RMSNorm in the prologue (normw != null),
 // epilogue by destination: out_f32 [R][N] | h (in-place residual add) | ff (SwiGLU gate of the Wa/Wb row pair)
