@@ -95,6 +95,16 @@ int  lg_prefill(lg_engine* e, const void* cond, const float* emb_mask, int B, in
  * under CFG both halves consume the same token (torch.cat([x, x])). logits_out f32 [rows, V]. */
 int  lg_decode_step(lg_engine* e, const int32_t* tokens, int B, int pos, int use_cfg,
                     float* logits_out, void* stream);
+/* Iteration-level scheduling for class-conditional serving (autoregressive/serve/llm_engine.py:511 `step()`, serve/llm.py:238-266):
+ * ONE decode step for sequences at DIFFERENT depths. pos_rows dev int32 [R]: position of every row (R = 2B under CFG, cond rows
+ * first); a row at position 0 has just joined and takes its class embedding (cond rows: tokens[b] is the label, uncond rows: the
+ * null class), any other row the embedding of tokens[b]. Writes row r's K/V at pos_rows[r] and attends over [0, pos_rows[r]].
+ * logits_out dev f32 [R, V]. */
+int  lg_decode_rows(lg_engine* e, const int32_t* tokens, const int32_t* pos_rows, int B, int use_cfg, float* logits_out, void* stream);
+/* lg_sample with per-request RNG streams: image b draws with seed_rows[b] at token index step_rows[b] (exactly the draw a
+ * batch-of-one lg_generate with that seed makes), result -> out_idx[b] and/or out_seq[b*seq_stride + step_rows[b]]. */
+int  lg_sample_rows(const float* logits, int B, int V, int mix_cfg, int round_dtype, const lg_sample_cfg* sc, const uint64_t* seed_rows,
+                    const int32_t* step_rows, int32_t* out_idx, int32_t* out_seq, int seq_stride, void* stream);
 /* Fused CFG-mix + temperature + top-k + top-p + softmax + (argmax | multinomial): generate.py:57-66,95-97.
  * logits f32 [rows, V] (rows = 2B when mix_cfg, cond rows first); writes out_idx int32 [B] and, when
  * non-NULL, out_probs f32 [B, V] (the post-filter softmax the reference returns as `probs`).

@@ -46,6 +46,7 @@ struct AttnTmaArgs {
     bf16* out;         // [R, D]
     int R, H, maxS;
     const int* pos_dev; int pos_value;
+    const int* pos_rows;         // per-row positions [R] or null (continuous batching)
     long long row_base;          // first cache row of this layer inside the tensor maps
     const float* emb_mask; int B, Tc;
     float scale;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(kWarps * 32 * (NST > 2 ? NST : 1), NST > 2 ? 1
     __syncthreads();
     // Programmatic dependent launch: the position counter and every key row of EARLIER steps were produced at least
     // one kernel before the predecessor, so their TMA loads are issued before the dependency wait.
-    const int qpos = (a.pos_dev ? *a.pos_dev : 0) + a.pos_value;
+    const int qpos = a.pos_rows ? a.pos_rows[r] : (a.pos_dev ? *a.pos_dev : 0) + a.pos_value;
     const int nkeys = FUSED ? qpos : qpos + 1;      // keys streamed from the cache (FUSED: the new key stays on chip)
     const int nchunks = (nkeys + kKC - 1) / kKC;
 
@@ -522,7 +523,7 @@ bool attn_tma_supported(const AttnArgs& a) {
 int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     AttnTmaArgs t;
     t.q = (const bf16*)a.q; t.out = (bf16*)a.out; t.R = a.R; t.H = a.H; t.maxS = a.maxS;
-    t.pos_dev = a.pos.dev; t.pos_value = a.pos.value; t.row_base = a.cache_row_base;
+    t.pos_dev = a.pos.dev; t.pos_value = a.pos.value; t.pos_rows = a.pos.rows; t.row_base = a.cache_row_base;
     t.emb_mask = a.emb_mask; t.B = a.B; t.Tc = a.Tc; t.scale = a.scale;
     t.partial = a.qkv_partial; t.ksplit = a.qkv_ksplit; t.freqs = a.freqs;
     t.kcache = (bf16*)const_cast<void*>(a.kcache); t.vcache = (bf16*)const_cast<void*>(a.vcache);
@@ -541,7 +542,7 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     // v2 (persistent warp-per-item, LG_ATTN_V2=1) measured SLOWER than the CTA-per-item kernel on B200 (25.7 vs
     // 19.1 us at R=128, c=128: with one warp per scheduler the ldmatrix->mma->softmax chain is latency-bound), so it
     // stays opt-in; profiles/ keeps both ncu captures.
-    const bool v2 = lg_env_flag("LG_ATTN_V2", 0) && a.R * a.H >= 4 * 148 && a.hd == 64;
+    const bool v2 = lg_env_flag("LG_ATTN_V2", 0) && a.R * a.H >= 4 * 148 && a.hd == 64 && !a.pos.rows;
     if (v2) return launch_v2<64>(km, vm, t, st);
     if (a.hd == 64) return launch_t<64, false>(km, vm, km16, vm16, t, st);
     return launch_t<128, false>(km, vm, km16, vm16, t, st);

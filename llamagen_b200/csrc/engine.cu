@@ -593,6 +593,37 @@ int lg_decode_step(lg_engine* e, const int32_t* tokens, int B, int pos, int use_
     return 0;
 }
 
+int lg_decode_rows(lg_engine* e, const int32_t* tokens, const int32_t* pos_rows, int B, int use_cfg, float* logits_out, void* stream) {
+    // Iteration-level scheduling (serve/llm_engine.py:511 step()): one forward for R rows that sit at DIFFERENT depths. A row at
+    // position 0 is a request that has just joined: it takes its class embedding (the c2i "prefill" is that single position).
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = use_cfg ? 2 * B : B;
+    LG_REQUIRE(e, "lg_decode_rows: null engine");
+    DeviceGuard guard(e->device);
+    LG_TRY(check_ready(e, R, 1));
+    LG_TRY(e->zero_fill_if_needed(st));
+    LG_REQUIRE(tokens && pos_rows && logits_out && B > 0, "lg_decode_rows: bad argument");
+    LG_REQUIRE(e->cfg.model_type == LG_MODEL_C2I && e->cfg.cls_token_num == 1, "lg_decode_rows: class-conditional models only");
+    LG_TRY(launch_embed_rows(e->cls_table, e->tok_emb, tokens, pos_rows, B, R, e->cfg.num_classes, e->cfg.dim, e->cfg.dtype, e->ws.h, st));
+    PosArg p{nullptr, 0, pos_rows};
+    e->pd_tokens = nullptr;
+    LG_TRY(e->forward(R, 1, p, nullptr, B, logits_out, false, st));
+    if (e->cfg.dtype == LG_DTYPE_BF16) LG_TRY(round_logits_inplace(logits_out, (size_t)R * e->cfg.vocab_size, st));
+    return 0;
+}
+
+int lg_sample_rows(const float* logits, int B, int V, int mix_cfg, int round_dtype, const lg_sample_cfg* sc, const uint64_t* seed_rows,
+                   const int32_t* step_rows, int32_t* out_idx, int32_t* out_seq, int seq_stride, void* stream) {
+    LG_REQUIRE(logits && sc && seed_rows && step_rows && (out_idx || out_seq), "lg_sample_rows: null argument");
+    SampleArgs a{};
+    a.logits = logits; a.B = B; a.V = V; a.mix_cfg = mix_cfg; a.round_bf16 = round_dtype == LG_DTYPE_BF16;
+    a.cfg_scale = sc->cfg_scale; a.cfg_interval = sc->cfg_interval; a.temperature = sc->temperature;
+    a.top_k = sc->top_k; a.top_p = sc->top_p; a.greedy = sc->greedy; a.seed = sc->seed; a.step = 0;
+    a.seed_rows = seed_rows; a.step_rows = step_rows;
+    a.out_idx = out_idx; a.out_seq = out_seq; a.seq_stride = seq_stride;
+    return launch_sample(a, (cudaStream_t)stream);
+}
+
 int lg_sample(const float* logits, int B, int V, int mix_cfg, int round_dtype, const lg_sample_cfg* sc, uint64_t step,
               int32_t* out_idx, float* out_probs, void* stream) {
     LG_REQUIRE(logits && sc && out_idx, "lg_sample: null argument");

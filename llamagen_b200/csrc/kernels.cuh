@@ -28,6 +28,9 @@ struct SampleArgs {
     const int32_t* teacher;// [B, seq_stride] or null: teacher-forced next token
     float* dbg_logits;     // [S, dbg_batch, V] or null: mixed logits before temperature (row = row_offset + b)
     int dbg_batch;         // total images in the dbg buffer (0 -> B)
+    // continuous batching (lg_sample_rows): every image is its own request with its own RNG seed and token index
+    const uint64_t* seed_rows = nullptr;   // [B] or null
+    const int* step_rows = nullptr;        // [B] or null
 };
 int launch_sample(const SampleArgs& a, cudaStream_t st);
 
@@ -51,14 +54,19 @@ int gemm_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_s
 // ------------------------------------------------------------------------------------------------
 // xf_kernels.cu — transformer glue kernels (all templated on the activation dtype internally)
 // ------------------------------------------------------------------------------------------------
-struct PosArg {            // position of row-block: pos = (dev ? *dev : value) + t
+struct PosArg {            // position of row-block: pos = (rows ? rows[r] : (dev ? *dev : 0) + value) + t
     const int* dev;
     int value;
+    const int* rows = nullptr;   // per-row positions [R] (continuous batching: sequences at different depths share one step)
 };
 
 // out[r,:] = table[idx(r),:]; idx(r) = r < B ? src[r] : (null_idx >= 0 ? null_idx : src[r-B])
 int launch_embed(const void* table, const int32_t* src, int B, int R, int null_idx, int D, int dtype,
                  void* out, cudaStream_t st);
+// continuous batching, c2i: row r at position 0 takes the class embedding (cond rows: label src[r], uncond rows: null_idx),
+// at any other position the token embedding of src[r % B]
+int launch_embed_rows(const void* cls_table, const void* tok_table, const int32_t* src, const int* pos_rows, int B, int R, int null_idx,
+                      int D, int dtype, void* out, cudaStream_t st);
 // t2i cond rows: out[(r*T+t),:] = r < B ? cond[r,t,:] : uncond[t,:]   (generate.py:137)
 int launch_build_caption_rows(const void* cond, const void* uncond, int B, int R, int T, int C, int dtype,
                               void* out, cudaStream_t st);

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int V = a.V, B = a.B;
-    const uint64_t step = a.step_dev ? (uint64_t)(*a.step_dev) : a.step;
+    const uint64_t step = a.step_rows ? (uint64_t)a.step_rows[b] : (a.step_dev ? (uint64_t)(*a.step_dev) : a.step);
 
     bool mix = a.mix_cfg != 0;
     // generate.py:113-114 — decode iteration i = step-1; once i > cfg_interval the mix is dropped.
@@ -371,8 +371,10 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
         __syncthreads();
         const float total = red[32];
         const float excl = s_wtot[warp] + (incl - local);
-        const uint64_t r = splitmix64(splitmix64(a.seed ^ (0xA0761D6478BD642Full * (step + 1))) ^
-                                      (0xE7037ED1A0B428DBull * (uint64_t)(b + 1 + a.row_offset)));
+        // per-request streams (seed_rows): every image draws exactly what a batch-of-one generate() with its seed would draw
+        const uint64_t seed = a.seed_rows ? a.seed_rows[b] : a.seed;
+        const uint64_t rrow = a.seed_rows ? 1ull : (uint64_t)(b + 1 + a.row_offset);
+        const uint64_t r = splitmix64(splitmix64(seed ^ (0xA0761D6478BD642Full * (step + 1))) ^ (0xE7037ED1A0B428DBull * rrow));
         const float u = (float)(r >> 40) * (1.0f / 16777216.0f);
         const float target = u * total;
         if (local > 0.f && target >= excl && target < excl + local) {

@@ -12,7 +12,7 @@ namespace {
 
 template <typename T> using TR = ElemTraits<T>;
 
-__device__ __forceinline__ int load_pos(const PosArg& p) { return (p.dev ? *p.dev : 0) + p.value; }
+__device__ __forceinline__ int load_pos(const PosArg& p, int r) { return p.rows ? p.rows[r] : (p.dev ? *p.dev : 0) + p.value; }
 
 __device__ __forceinline__ float sum_partials(const float* __restrict__ p, size_t idx, int ks, size_t slab) {
     float s = p[idx];
@@ -28,6 +28,17 @@ __global__ void embed_kernel(const T* __restrict__ table, const int32_t* __restr
     const int r = blockIdx.x;
     const int idx = r < B ? src[r] : (null_idx >= 0 ? null_idx : src[r - B]);
     const T* s = table + (size_t)idx * D;
+    T* d = out + (size_t)r * D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) d[i] = s[i];
+}
+
+// continuous batching (c2i): per-row choice between the class table (position 0) and the token table
+template <typename T>
+__global__ void embed_rows_kernel(const T* __restrict__ cls_table, const T* __restrict__ tok_table, const int32_t* __restrict__ src,
+                                  const int* __restrict__ pos_rows, int B, int null_idx, int D, T* __restrict__ out) {
+    lg_pdl_sync();
+    const int r = blockIdx.x, b = r < B ? r : r - B;
+    const T* s = pos_rows[r] == 0 ? cls_table + (size_t)(r < B ? src[b] : null_idx) * D : tok_table + (size_t)src[b] * D;
     T* d = out + (size_t)r * D;
     for (int i = threadIdx.x; i < D; i += blockDim.x) d[i] = s[i];
 }
@@ -98,7 +109,7 @@ template <typename T>
 __global__ void __launch_bounds__(1024) qkv_epilogue_kernel(QkvEpiArgs a) {
     lg_pdl_sync();
     const int m = blockIdx.x, r = m / a.Tq, t = m % a.Tq;
-    const int p = load_pos(a.pos) + t;
+    const int p = load_pos(a.pos, r) + t;
     const int D = a.D, hd = a.hd, half = hd >> 1, N = 3 * D;
     const size_t slab = (size_t)a.M * N;
     const float* fr = a.freqs + (size_t)p * half * 2;
@@ -213,7 +224,7 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
     extern __shared__ float smem[];  // [nwarps][HD + 2]
     const int h = blockIdx.x, m = blockIdx.y;
     const int r = m / a.Tq, t = m - r * a.Tq;
-    const int qpos = load_pos(a.pos) + t;
+    const int qpos = load_pos(a.pos, r) + t;
     const int nkeys = qpos + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane / LPK, li = lane - g * LPK;
@@ -337,6 +348,14 @@ int launch_embed(const void* table, const int32_t* src, int B, int R, int null_i
         dtype,
         [&] { (void)lg_launch(embed_kernel<float>, dim3(R), dim3(128), 0, st, (const float*)table, src, B, null_idx, D, (float*)out); LG_LAUNCH_CHECK(); return 0; },
         [&] { (void)lg_launch(embed_kernel<bf16>, dim3(R), dim3(128), 0, st, (const bf16*)table, src, B, null_idx, D, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
+}
+
+int launch_embed_rows(const void* cls_table, const void* tok_table, const int32_t* src, const int* pos_rows, int B, int R, int null_idx,
+                      int D, int dtype, void* out, cudaStream_t st) {
+    return dispatch_dtype(
+        dtype,
+        [&] { (void)lg_launch(embed_rows_kernel<float>, dim3(R), dim3(128), 0, st, (const float*)cls_table, (const float*)tok_table, src, pos_rows, B, null_idx, D, (float*)out); LG_LAUNCH_CHECK(); return 0; },
+        [&] { (void)lg_launch(embed_rows_kernel<bf16>, dim3(R), dim3(128), 0, st, (const bf16*)cls_table, (const bf16*)tok_table, src, pos_rows, B, null_idx, D, (bf16*)out); LG_LAUNCH_CHECK(); return 0; });
 }
 
 int launch_build_caption_rows(const void* cond, const void* uncond, int B, int R, int T, int C, int dtype, void* out,

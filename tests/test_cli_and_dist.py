@@ -133,34 +133,56 @@ def test_t2i_ddp_prompt_sharding(tmp_path):
     assert sorted(seen) == list(range(12))
 
 
-def test_serve_queue_batches_and_pairs_cfg_twins(monkeypatch):
-    """Host logic of serve.LLM with the engine call stubbed: batches split at max_num_seqs and at a change of sampling
-    parameters, null-class twins mirror their conditional request, outputs come back sorted by request id."""
+def test_serve_continuous_batching_host_logic():
+    """Host logic of serve.LLM with the device step stubbed (next token = input + 1): requests JOIN MID-SEQUENCE of the running ones
+    (iteration-level scheduling, llm_engine.py:511), a change of sampling parameters waits for the running set to drain, null-class
+    twins mirror their conditional request, outputs come back sorted by request id."""
     import types
     import torch
     from llamagen_b200 import serve
-    calls = []
+    model = types.SimpleNamespace(model_type="c2i", tok_embeddings=types.SimpleNamespace(weight=torch.zeros(1)), vocab_size=64,
+                                  cls_token_num=1, setup_caches=lambda **kw: None)
 
-    def fake_generate(model, cond, max_new_tokens, **kw):
-        calls.append((cond.tolist(), max_new_tokens, kw["top_k"], kw["cfg_scale"]))
-        return cond[:, None].repeat(1, max_new_tokens)
+    def fake_device_step(self, st, params):
+        B = self.max_num_seqs
+        nxt = st["tok"] + 1
+        for b in range(B):
+            st["out"][b, int(st["pos"][b])] = nxt[b]
+        st["tok"].copy_(nxt)
 
-    monkeypatch.setattr(serve, "generate", fake_generate)
-    model = types.SimpleNamespace(model_type="c2i", tok_embeddings=types.SimpleNamespace(weight=torch.zeros(1)))
-    llm = serve.LLM(model, cfg_scale=4.0, num_classes=1000, max_num_seqs=2)
-    a, b = serve.SamplingParams(top_k=10, max_tokens=3), serve.SamplingParams(top_k=20, max_tokens=3)
-    labels = [5, 6, 7, 8]
-    outs = llm.generate(prompt_token_ids=[[c] for c in labels] + [[1000]] * 4, sampling_params=[a, a, a, b] * 2)
-    assert calls == [([5, 6], 3, 10, 4.0), ([7], 3, 10, 4.0), ([8], 3, 20, 4.0)]
-    assert [o.request_id for o in outs] == [str(i) for i in range(8)]
-    assert [o.outputs[0].token_ids[0] for o in outs] == labels + labels
-    assert [o.prompt_token_ids for o in outs[4:]] == [[1000]] * 4
-    assert not llm.has_unfinished_requests() and llm.get_num_unfinished_requests() == 0
-    import pytest
-    with pytest.raises(ValueError):
-        llm.generate(prompt_token_ids=[[1], [2]])
-    with pytest.raises(ValueError):
-        llm.generate(prompts=["a"], prompt_token_ids=[[1]])
+    serve.LLM._device_step, saved = fake_device_step, serve.LLM._device_step
+    try:
+        a, b = serve.SamplingParams(top_k=10, max_tokens=3), serve.SamplingParams(top_k=20, max_tokens=3)
+        # --- mid-sequence join: r2 arrives after the first step and starts while r0, r1 are at depth 1
+        llm = serve.LLM(model, cfg_scale=1.0, num_classes=1000, max_num_seqs=3, seed=0)
+        llm.add_request([5], a)
+        llm.add_request([6], a)
+        outs = llm.step()
+        assert outs == [] and llm._depth[:2] == [1, 1]
+        llm.add_request([40], a)
+        while llm.has_unfinished_requests():
+            outs += llm.step()
+        assert llm.steps_run == 4                             # static batching would need 3 + 3 steps
+        got = {o.request_id: o.outputs[0].token_ids for o in outs}
+        assert got == {"0": [6, 7, 8], "1": [7, 8, 9], "2": [41, 42, 43]}
+        # --- LLM.generate surface: CFG twins, parameter change, more requests than slots
+        llm = serve.LLM(model, cfg_scale=4.0, num_classes=1000, max_num_seqs=2, seed=0)
+        labels = [5, 6, 7, 8]
+        outs = llm.generate(prompt_token_ids=[[c] for c in labels] + [[1000]] * 4, sampling_params=[a, a, a, b] * 2)
+        assert [o.request_id for o in outs] == [str(i) for i in range(8)]
+        assert [o.outputs[0].token_ids for o in outs[:4]] == [[c + 1, c + 2, c + 3] for c in labels]
+        assert [o.outputs[0].token_ids for o in outs[4:]] == [o.outputs[0].token_ids for o in outs[:4]]
+        assert [o.prompt_token_ids for o in outs[4:]] == [[1000]] * 4
+        # r0, r1 run together (3 steps); r2 joins a fresh set (3 steps); r3 has other sampling parameters: it waits for the drain (3 steps)
+        assert llm.steps_run == 9
+        assert not llm.has_unfinished_requests() and llm.get_num_unfinished_requests() == 0
+        import pytest
+        with pytest.raises(ValueError):
+            llm.generate(prompt_token_ids=[[1], [2]])
+        with pytest.raises(ValueError):
+            llm.generate(prompts=["a"], prompt_token_ids=[[1]])
+    finally:
+        serve.LLM._device_step = saved
 
 
 def test_left_pad_and_index_map_properties():

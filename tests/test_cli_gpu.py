@@ -95,9 +95,11 @@ def test_sample_t2i_ddp_cli_single_rank(tmp_path, monkeypatch, mode):
     assert open(os.path.join(folder, "captions.txt")).read().splitlines()[4] == "a photo of thing 4"
 
 
-def test_serve_llm_generate_matches_generate():
-    """serve.LLM (the reference's LLM.generate call surface, serve/sample_c2i.py:35-67) == generate() on the same seeds;
-    requests beyond max_num_seqs are served by later engine steps and come back sorted by request id."""
+def test_serve_llm_continuous_batching_matches_independent_generate():
+    """serve.LLM with iteration-level scheduling (llm_engine.py:511): requests JOIN MID-SEQUENCE of running ones (per-row positions in
+    lg_decode_rows) and every request must receive exactly the tokens an INDEPENDENT generate() call with its seed produces.
+    The reference point is generate() on max_num_seqs copies of the label (same row count -> same GEMM plan, row 0 draws with
+    (seed, step, row 1) exactly like the request's RNG stream), so the comparison is bit-for-bit, sampling included."""
     import torch
     from llamagen_b200 import GPT_models, generate
     from llamagen_b200.serve import LLM, SamplingParams
@@ -105,21 +107,40 @@ def test_serve_llm_generate_matches_generate():
     gpt = GPT_models["GPT-B"](vocab_size=16384, block_size=64, num_classes=1000, cls_token_num=1, model_type="c2i")
     gpt = gpt.to("cuda", torch.bfloat16).eval()
     gpt.output.weight.data.normal_(std=0.02)
-    labels = [207, 360, 387, 974, 88, 979]
-    prompts = [[c] for c in labels] + [[1000] for _ in labels]
-    sp = SamplingParams(temperature=1.0, top_p=1.0, top_k=2000, max_tokens=64)
-    llm = LLM(gpt, cfg_scale=4.0, num_classes=1000, max_num_seqs=4, seed=11)
-    outs = llm.generate(prompt_token_ids=prompts, sampling_params=sp)
-    assert [o.request_id for o in outs] == [str(i) for i in range(12)]
-    assert all(o.finished and len(o.outputs[0].token_ids) == 64 for o in outs)
-    toks = torch.tensor([o.outputs[0].token_ids for o in outs])
+    S, slots = 64, 8
+    sp = SamplingParams(temperature=1.0, top_p=1.0, top_k=2000, max_tokens=S)
+    llm = LLM(gpt, cfg_scale=4.0, num_classes=1000, max_num_seqs=slots, seed=11)
+    labels = [207, 360, 387, 974, 88, 979, 417, 279, 1, 2, 3]
+    # three waves: 3 requests, 17 steps later 5 more (join at depth 17 of the first wave), 30 steps later the rest; 11 requests > 8 slots
+    outs = []
+    for c in labels[:3]:
+        llm.add_request([c], sp)
+    for _ in range(17):
+        outs += llm.step()
+    for c in labels[3:8]:
+        llm.add_request([c], sp)
+    for _ in range(30):
+        outs += llm.step()
+    for c in labels[8:]:
+        llm.add_request([c], sp)
+    while llm.has_unfinished_requests():
+        outs += llm.step()
+    # wave 1 ends at step 64; all 8 slots were busy, so wave 3 joins at step 65 (wave 2 is then at depth 47) and ends at step 128
+    assert llm.steps_run == 2 * S
+    got = {int(o.request_id): o.outputs[0].token_ids for o in outs}
+    assert sorted(got) == list(range(len(labels))) and all(len(t) == S for t in got.values())
+    for rid, c in enumerate(labels):
+        ref = generate(gpt, torch.full((slots,), c, device="cuda"), S, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, seed=11 + rid)
+        assert ref[0].cpu().tolist() == got[rid], rid
+    # LLM.generate surface (serve/sample_c2i.py:35-67): CFG twins get their conditional request's tokens, sorted by request id
+    llm2 = LLM(gpt, cfg_scale=4.0, num_classes=1000, max_num_seqs=4, seed=5)
+    prompts = [[c] for c in labels[:6]] + [[1000] for _ in range(6)]
+    res = llm2.generate(prompt_token_ids=prompts, sampling_params=sp)
+    assert [o.request_id for o in res] == [str(i) for i in range(12)]
+    toks = torch.tensor([o.outputs[0].token_ids for o in res])
     assert torch.equal(toks[:6], toks[6:])
-    dev = "cuda"
-    a = generate(gpt, torch.tensor(labels[:4], device=dev), 64, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, seed=11)
-    b = generate(gpt, torch.tensor(labels[4:], device=dev), 64, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, seed=12)
-    assert torch.equal(toks[:6], torch.cat([a, b]).cpu().long())
     with pytest.raises(ValueError):
-        llm.generate(prompt_token_ids=[[1], [2]], sampling_params=sp)        # cfg on but no null-class twins
+        llm2.generate(prompt_token_ids=[[1], [2]], sampling_params=sp)        # cfg on but no null-class twins
     with pytest.raises(ValueError):
         LLM(gpt, cfg_scale=1.0).generate(prompt_token_ids=[[1, 2]])
 
