@@ -172,7 +172,7 @@ def kernel_class(name: str) -> str:
         return "vq_conv_gemm"
     if "EpiVq" in n or "softmax_rows" in n:
         return "vq_attn"
-    if "gemm_tc" in n or "gemm_skinny" in n or "gemm_mma_kernel" in n or "gemv_small" in n:
+    if "gemm_tc" in n or "gemm_dx" in n or "gemm_skinny" in n or "gemm_mma_kernel" in n or "gemv_small" in n:
         return "dense_gemm"
     if "decode_small" in n:
         return "persistent_decode"

@@ -179,6 +179,13 @@ const char* lg_profile_class_name(int cls);   /* NULL past the last class */
 int  lg_test_gemm(const void* x, const void* w, int M, int N, int K, int dtype, float* y,
                   void* dev_scratch, size_t scratch_bytes, void* stream);
 
+/* The decode step's direct-epilogue GEMM (csrc/gemm_dx.cu) on its own. mode 0: y (f32 [M,N]) = norm(x) * wa^T; mode 1: h (bf16
+ * [M,N], in place) = bf16(h + bf16(norm(x) * wa^T)) — the residual add of gpt.py:255-256; mode 2: ff (bf16 [M,N]) =
+ * silu(norm(x) * wa^T) * (norm(x) * wb^T) — gpt.py:167. norm(x) = RMSNorm(x) * normw (gpt.py:143-148) when normw != NULL, else x.
+ * x [M,K], wa/wb [N,K], normw [K]: bf16 device pointers. */
+int  lg_test_gemm_dx(const void* x, const void* wa, const void* wb, int M, int N, int K, int mode, const void* normw,
+                     float eps, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

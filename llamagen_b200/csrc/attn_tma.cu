@@ -20,7 +20,11 @@ using namespace tma;
 constexpr int kKC = LG_ATTN_KC;   // keys per stage (64 -> 4 warps, 6 CTAs/SM; 48 -> 3 warps, 8 CTAs/SM)
 constexpr int kStagesA = 2;       // 2 stages of K+V per CTA; contexts here are <= 1144 keys
 constexpr int kWarps = kKC / 16;  // each warp owns 16 keys of a stage
-constexpr int kCtasPerSm64 = kKC == 48 ? 8 : 6;
+#ifdef LG_ATTN_CTAS
+constexpr int kCtasPerSm64 = LG_ATTN_CTAS;
+#else
+constexpr int kCtasPerSm64 = kKC == 48 ? 8 : (kKC == 32 ? 10 : 6);
+#endif
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
@@ -62,8 +66,8 @@ struct AttnTmaArgs {
 // (for future steps) and attends to it straight from shared memory. Every TMA load then only touches rows written
 // in EARLIER steps, so the whole KV stream is requested before the programmatic-dependency wait and overlaps the
 // QKV GEMM; one dependent kernel per layer disappears.
-template <int HD, bool FUSED, int NST>
-__global__ void __launch_bounds__(kWarps * 32 * (NST > 2 ? NST : 1), NST > 2 ? 1 : (HD == 64 ? kCtasPerSm64 : 3)) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
+template <int HD, bool FUSED, int NST, bool PAR_ = (NST > 2)>
+__global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD == 64 ? (NST > 2 ? 4 : kCtasPerSm64) : 3)) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
                                                                const __grid_constant__ CUtensorMap vmap,
                                                                const __grid_constant__ CUtensorMap kmap16,
                                                                const __grid_constant__ CUtensorMap vmap16, AttnTmaArgs a) {
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(kWarps * 32 * (NST > 2 ? NST : 1), NST > 2 ? 1
     constexpr int TILE_BYTES = NSUB * SUB_BYTES;  // K (or V) of one stage
     // NST > 2 (few work items, batch-1 latency path): one warp group per ring stage, so the chunks of a context are processed
     // concurrently instead of one after the other; a stage is private to its group (named barrier, no CTA-wide sync per chunk)
-    constexpr bool PAR = NST > 2;
+    constexpr bool PAR = PAR_;
     constexpr int NW = PAR ? NST * kWarps : kWarps;
     constexpr int NSLOT = NW + (FUSED ? 1 : 0);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -489,19 +493,19 @@ int launch_v2(const CUtensorMap& kmap, const CUtensorMap& vmap, const AttnTmaArg
     return 0;
 }
 
-template <int HD, bool FUSED, int NST = kStagesA>
+template <int HD, bool FUSED, int NST = kStagesA, bool PAR = (NST > 2)>
 int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const CUtensorMap& kmap16, const CUtensorMap& vmap16,
              const AttnTmaArgs& a, cudaStream_t st) {
     constexpr int TILE_BYTES = (HD / 64) * kKC * 128;
-    constexpr int NW = NST > 2 ? NST * kWarps : kWarps;
+    constexpr int NW = PAR ? NST * kWarps : kWarps;
     const size_t smem = 1024 + (size_t)NST * 2 * TILE_BYTES + NST * sizeof(uint64_t) +
                         (NW + 1) * (HD + 2) * sizeof(float) + 3 * HD * sizeof(bf16) + 16;
     static DevOnce attr;
     if (lg_first_on_device(attr)) {
-        LG_CUDA_OK(cudaFuncSetAttribute(attn_tma_kernel<HD, FUSED, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LG_CUDA_OK(cudaFuncSetAttribute(attn_tma_kernel<HD, FUSED, NST, PAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     dim3 grid(a.H, a.R);
-    (void)lg_launch(attn_tma_kernel<HD, FUSED, NST>, dim3(grid), dim3(NW * 32), smem, st, kmap, vmap, kmap16, vmap16, a);
+    (void)lg_launch(attn_tma_kernel<HD, FUSED, NST, PAR>, dim3(grid), dim3(NW * 32), smem, st, kmap, vmap, kmap16, vmap16, a);
     LG_LAUNCH_CHECK();
     return 0;
 }
@@ -536,6 +540,10 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
         // few (row, head) items (batch-1 latency path): a 6-stage ring holds a whole 288-key context, so every K/V byte is
         // requested before the dependency wait instead of two stages at a time
         if (a.hd == 64 && a.R * a.H <= 2 * 148 && lg_env_flag("LG_ATTN_DEEP", 1)) return launch_t<64, true, 6>(km, vm, km16, vm16, t, st);
+        // deeper sequential ring (A/B switch): more keys requested before the dependency wait, fewer refill round trips
+        const int nst = lg_env_flag("LG_ATTN_NST", 2);
+        if (a.hd == 64 && nst == 3) return launch_t<64, true, 3, false>(km, vm, km16, vm16, t, st);
+        if (a.hd == 64 && nst == 4) return launch_t<64, true, 4, false>(km, vm, km16, vm16, t, st);
         if (a.hd == 64) return launch_t<64, true>(km, vm, km16, vm16, t, st);
         return launch_t<128, true>(km, vm, km16, vm16, t, st);
     }

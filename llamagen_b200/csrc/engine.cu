@@ -138,7 +138,7 @@ struct lg_engine {
     const float* freqs = nullptr;
     bool finalized = false;
     Workspace ws;                         // ACTIVE workspace (full, or one of the two halves while a group is issued)
-    static constexpr int kMaxChains = 4;
+    static constexpr int kMaxChains = 8;
     Workspace full, sub[kMaxChains];      // sub[g]: rows/n_sub each, carved INSIDE the regions of `full` (multi-chain decode)
     int n_sub = 0;                        // 0: no split available
     bool use_graph = true;
@@ -146,8 +146,8 @@ struct lg_engine {
     const int32_t* pd_tokens = nullptr;   // set by the caller of forward() when the step's token ids are in device memory and the
                                           // embedding lookup has NOT been launched (the persistent kernel gathers the rows itself)
     bool ws_needs_zero = false;           // KV cache + counters of `full` still have to be zero-filled (done on the caller's stream)
-    cudaStream_t works[kMaxChains] = {nullptr, nullptr, nullptr, nullptr};   // engine-owned streams (one per chain)
-    cudaEvent_t ev_fork = nullptr, ev_joins[kMaxChains] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t works[kMaxChains] = {};   // engine-owned streams (one per chain)
+    cudaEvent_t ev_fork = nullptr, ev_joins[kMaxChains] = {};
     ~lg_engine() {
         for (int i = 0; i < kMaxChains; ++i) {
             if (works[i]) cudaStreamDestroy(works[i]);
@@ -213,7 +213,7 @@ size_t lg_engine::carve(Workspace& o, char* base, int rows, int max_seq) const {
     o.partial = (float*)take(pf * sizeof(float));
     o.logits = (float*)take((size_t)rows * V * sizeof(float));
     o.tokens = (int32_t*)take((size_t)rows * sizeof(int32_t));
-    o.counters = (int*)take(128 * sizeof(int));   // [0, 8): pos/step per chain; [96, 98): grid-barrier counters of decode_persist.cu
+    o.counters = (int*)take(128 * sizeof(int));   // [0, 16): pos/step per chain (<= 8 chains); [96, 98): grid-barrier counters of decode_persist.cu
     o.rows = rows;
     o.max_seq = max_seq;
     return off;
@@ -290,6 +290,11 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         return 0;
     }
     LG_PROF(PC_EMBED_MISC, st, launch_rmsnorm(ws.h, layers[0].attn_norm, ws.xn, M, D, cfg.norm_eps, dt, st));
+    // Direct-epilogue GEMMs (gemm_dx.cu, 6 kernels per layer instead of 8) are validated but OFF by default: a CTA that owns the full
+    // reduction issues 64 dependent tcgen05.mma steps (~0.37 us per 64-wide k-block whatever the UMMA N, measured), so each of the
+    // two kernels costs 10-13 us against 4.4 + 3.2 us for the split-K GEMM + row kernel it replaces (392 vs 292 ms/step).
+    const bool dx = Tq == 1 && M <= 256 && lg_env_flag("LG_DIRECT", 0) && gemm_dx_supported(M, D, D, dt, DX_RESID, false) &&
+                        gemm_dx_supported(M, F, D, dt, DX_SWIGLU, true);
     for (int l = 0; l < L; ++l) {
         const Layer& ly = layers[l];
         char* kc = ws.kcache + (size_t)l * ws.layer_cache_bytes;
@@ -313,10 +318,19 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
             LG_PROF(PC_QKV_EPI, st, launch_qkv_epilogue(qa, st));
         }
         LG_PROF(PC_ATTENTION, st, launch_attention(aa, st));
-        LG_PROF(PC_GEMM_WO, st, gemm(ws.attn, M, D, D, ly.wo, nullptr, 0, &ks, nullptr, st, &nx_w13));
-        LG_PROF(PC_RESNORM, st, launch_residual_norm(ws.partial, ks, M, D, ws.h, ly.ffn_norm, ws.xn, cfg.norm_eps, dt, st));
-        LG_PROF(PC_GEMM_W13, st, gemm(ws.xn, M, 2 * F, D, ly.w1, ly.w3, F, &ks, nullptr, st, &nx_w2));
-        LG_PROF(PC_SILU, st, launch_silu_mul(ws.partial, ks, M, F, ws.ff, dt, st));
+        if (dx) {
+            // decode step: WO with the residual add in its drain, then w1|w3 with the RMSNorm on its resident rows and the SwiGLU
+            // gate in its drain (gemm_dx.cu) — two dependent kernels instead of four, no split-K slabs
+            GemmDx go{ws.attn, D, ly.wo, nullptr, M, D, D, DX_RESID, nullptr, 0.f, nullptr, ws.h, nullptr};
+            LG_PROF(PC_GEMM_WO, st, launch_gemm_dx(go, st, &nx_w13));
+            GemmDx g13{ws.h, D, ly.w1, ly.w3, M, F, D, DX_SWIGLU, ly.ffn_norm, cfg.norm_eps, nullptr, nullptr, ws.ff};
+            LG_PROF(PC_GEMM_W13, st, launch_gemm_dx(g13, st, &nx_w2));
+        } else {
+            LG_PROF(PC_GEMM_WO, st, gemm(ws.attn, M, D, D, ly.wo, nullptr, 0, &ks, nullptr, st, &nx_w13));
+            LG_PROF(PC_RESNORM, st, launch_residual_norm(ws.partial, ks, M, D, ws.h, ly.ffn_norm, ws.xn, cfg.norm_eps, dt, st));
+            LG_PROF(PC_GEMM_W13, st, gemm(ws.xn, M, 2 * F, D, ly.w1, ly.w3, F, &ks, nullptr, st, &nx_w2));
+            LG_PROF(PC_SILU, st, launch_silu_mul(ws.partial, ks, M, F, ws.ff, dt, st));
+        }
         LG_PROF(PC_GEMM_W2, st, gemm(ws.ff, M, D, F, ly.w2, nullptr, 0, &ks, nullptr, st, &nx_qkv));
         const void* next_norm = (l + 1 < L) ? layers[l + 1].attn_norm : final_norm;
         LG_PROF(PC_RESNORM, st, launch_residual_norm(ws.partial, ks, M, D, ws.h, next_norm, ws.xn, cfg.norm_eps, dt, st));
@@ -693,7 +707,7 @@ static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, 
     const lg_model_cfg& c = e->cfg;
 
     // Multi-chain decode: at large batch every kernel of a decode step is latency-bound (a few microseconds of
-    // dependent load -> compute -> store), so the batch is cut into LG_SPLIT (default 2, max 4) independent chains (their own KV-cache half,
+    // dependent load -> compute -> store), so the batch is cut into LG_SPLIT (default 2, max 8) independent chains (their own KV-cache half,
     // stream and CUDA graph) whose kernels interleave on the GPU. Each image's arithmetic is unchanged, so the result
     // is bit-identical to the single-chain run.
     const bool split = e->n_sub >= 2 && lg_env_flag("LG_SPLIT", 2) >= 2 && R == e->full.rows && B % e->n_sub == 0 &&
@@ -774,9 +788,9 @@ static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, 
         if (ce != cudaSuccess) return lg_fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
         return 0;
     };
-    cudaGraph_t g1[lg_engine::kMaxChains] = {nullptr, nullptr, nullptr, nullptr};
-    cudaGraphExec_t e1[lg_engine::kMaxChains] = {nullptr, nullptr, nullptr, nullptr};
-    uint64_t l1[lg_engine::kMaxChains] = {0, 0, 0, 0};
+    cudaGraph_t g1[lg_engine::kMaxChains] = {};
+    cudaGraphExec_t e1[lg_engine::kMaxChains] = {};
+    uint64_t l1[lg_engine::kMaxChains] = {};
     const int nbig = remaining / unroll, nsmall = remaining - nbig * unroll;
     for (int g = 0; g < nchains && ret == 0; ++g) {
         ret = capture(ch[g], unroll, &ch[g].graph, &ch[g].exec, &ch[g].per_step);
@@ -844,6 +858,16 @@ int lg_test_gemm(const void* x, const void* w, int M, int N, int K, int dtype, f
     GemmPlan plan;
     LG_TRY(gemm_partial(x, K, w, nullptr, 0, M, N, K, dtype, (float*)dev_scratch, &plan, st));
     return launch_reduce_f32((const float*)dev_scratch, plan.ksplit, M, N, y, st);
+}
+
+int lg_test_gemm_dx(const void* x, const void* wa, const void* wb, int M, int N, int K, int mode, const void* normw, float eps,
+                    void* out, void* stream) {
+    LG_REQUIRE(x && wa && out && mode >= DX_F32 && mode <= DX_SWIGLU, "lg_test_gemm_dx: bad argument");
+    GemmDx g{x, K, wa, wb, M, N, K, mode, normw, eps, nullptr, nullptr, nullptr};
+    if (mode == DX_F32) g.out_f32 = (float*)out;
+    else if (mode == DX_RESID) g.h = out;
+    else g.ff = out;
+    return launch_gemm_dx(g, (cudaStream_t)stream);
 }
 
 }  // extern "C"

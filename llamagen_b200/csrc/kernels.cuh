@@ -131,6 +131,22 @@ bool gemm_tc_supported(int M, int N, int K, int dtype);
 int gemm_tc_partial(const void* X, int ldx, const void* Wa, const void* Wb, int n_split, int M, int N, int K,
                     float* partial, int* ksplit_out, cudaStream_t st, const GemmNext* next = nullptr);
 
+// gemm_dx.cu — "direct" tcgen05 GEMM of the decode step: (feature tile) x (row block) CTAs over the FULL K (no split-K slab), the
+// activation rows resident in shared memory; optional RMSNorm prologue on those rows, epilogue by mode
+enum { DX_F32 = 0, DX_RESID = 1, DX_SWIGLU = 2 };
+struct GemmDx {
+    const void* X; int ldx;            // [M][K] bf16
+    const void* Wa; const void* Wb;    // [N][K] bf16; Wb only for DX_SWIGLU (w1 | w3, N = F)
+    int M, N, K;
+    int mode;
+    const void* normw; float eps;      // RMSNorm weight [K] applied to X (null: none)
+    float* out_f32;                    // DX_F32:    y [M][N]
+    void* h;                           // DX_RESID:  h[M][N] = bf16(h + bf16(y)) in place
+    void* ff;                          // DX_SWIGLU: ff[M][N] = silu(y1) * y3
+};
+bool gemm_dx_supported(int M, int N, int K, int dtype, int mode, bool norm);
+int launch_gemm_dx(const GemmDx& g, cudaStream_t st, const GemmNext* next = nullptr);
+
 // gemv_small.cu — decode GEMMs for R <= 8 rows: CTA-owned output columns (no split-K), RMSNorm in the prologue (normw != null),
 // epilogue by destination: out_f32 [R][N] | h (in-place residual add) | ff (SwiGLU gate of the Wa/Wb row pair)
 struct GemvSmall {

@@ -207,6 +207,29 @@ def test_multi_chain_decode_is_bit_identical(monkeypatch):
             assert torch.equal(outs[split][i], outs["1"][i]), (split, i)
 
 
+@pytest.mark.parametrize("B", [20, 64])
+def test_direct_epilogue_decode_path(B, monkeypatch):
+    """Decode steps with > 8 rows run WO and w1|w3 as direct-epilogue GEMMs (gemm_dx.cu: residual add / RMSNorm + SwiGLU fused,
+    6 kernels per layer). Same rounding points as the split-K slab path (only fp32 summation order differs): it must meet the
+    oracle bound (B = 20) and agree with the slab path on a teacher-forced stream, single- and dual-chain (B = 64 -> two chains)."""
+    m = _registry_model("GPT-L", torch.bfloat16, 5, block_size=256, vocab_size=16384)
+    torch.manual_seed(20 + B)
+    cond = torch.randint(0, 1000, (B,))
+    monkeypatch.setenv("LG_DIRECT", "1")
+    if B <= 20:
+        _bf16_parity(m, cond, 5)
+    teacher = torch.randint(0, 16384, (B, 10), generator=torch.Generator().manual_seed(B), dtype=torch.int32)
+    _, direct = _gen(m, cond, 10, None, cfg_scale=4.0, teacher=teacher.clone())
+    monkeypatch.setenv("LG_DIRECT", "0")
+    _, slab = _gen(m, cond, 10, None, cfg_scale=4.0, teacher=teacher.clone())
+    # two bf16 implementations with different fp32 summation orders (and rsqrt inputs): cfg 4.0 amplifies a flipped bf16 rounding
+    # ~7x, so the max is bounded like the oracle's own bf16-vs-fp32 spread (0.27 max / 0.03 mean at std 2-3 for GPT-L)
+    err = (direct - slab).abs()
+    scale = slab.std().item()
+    assert err.max().item() <= 0.15 * scale + 0.02, (err.max().item(), scale)
+    assert err.mean().item() <= 0.015 * scale + 0.002, (err.mean().item(), scale)
+
+
 @pytest.mark.parametrize("B", [1, 3, 4])
 def test_small_row_decode_path(B, monkeypatch):
     """R = 2B <= 8 rows take the column-owner tensor-core GEMV path (gemv_small.cu: RMSNorm in the prologue, residual /

@@ -47,3 +47,21 @@ def test_gemm(x, w):
     _lib.check(lib.lg_test_gemm(_lib.ptr(x), _lib.ptr(w), M, N, K, dt, _lib.ptr(y), _lib.ptr(scratch),
                                 ctypes.c_size_t(scratch.numel() * 4), _lib.current_stream(x.device)), "lg_test_gemm")
     return y
+
+
+def gemm_dx(x, wa, wb=None, mode=0, normw=None, eps=1e-5, h=None):
+    """The decode step's direct-epilogue GEMM (lg_test_gemm_dx): mode 0 -> y fp32, 1 -> h updated in place (returned), 2 -> ff."""
+    from llamagen_b200 import _lib
+    lib = _lib.load()
+    M, K = x.shape
+    N = wa.shape[0]
+    if mode == 0:
+        out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    elif mode == 1:
+        out = h.clone()
+    else:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.lg_test_gemm_dx(_lib.ptr(x), _lib.ptr(wa), _lib.ptr(wb) if wb is not None else None, M, N, K, mode,
+                                   _lib.ptr(normw) if normw is not None else None, ctypes.c_float(eps), _lib.ptr(out),
+                                   _lib.current_stream(x.device)), "lg_test_gemm_dx")
+    return out
