@@ -42,6 +42,7 @@ struct DxArgs {
     int nkb;              // k-blocks of 64
     int stages;           // weight ring depth
     int tmem_cols;
+    int ts;               // 1: the weight slice of every MMA step is copied smem -> TMEM (tcgen05.cp) and read from there (TS form)
     int nacc;             // independent TMEM accumulators the k-blocks rotate over (summed in the drain, fixed order)
     int mode, paired;
     const bf16* normw; float eps;
@@ -183,8 +184,26 @@ __global__ void __launch_bounds__(kThreadsDx, 1) gemm_dx_kernel(const __grid_con
                 // consecutive k-blocks go to different accumulators: tcgen05.mma into ONE accumulator is a dependent chain (~150 cycles
                 // per instruction at N <= 64, measured), independent accumulators let the operand fetches overlap
                 const uint32_t acc = tmem_base + (uint32_t)((i % a.nacc) * a.rblk);
-                for (int k = 0; k < kBK / 16; ++k)
-                    umma_bf16(acc, wdesc + (uint64_t)(2 * k), xdesc + (uint64_t)(2 * k), idesc, (uint32_t)((i >= a.nacc) | (k != 0)));
+                if (a.ts) {
+                    // TS form: in the SS form the tensor core fetches the 128 weight rows of every K=16 step from shared memory at
+                    // ~1 row per cycle (~0.37 us per k-block whatever N, profiles/r2_s9_dx_probe_*); tcgen05.cp moves the same 4 KB
+                    // slice into TMEM (128 lanes x 256 bit, a ring of 16 slots behind the accumulators) and the MMA reads A from there.
+                    // cp and mma execute in issue order, so no extra synchronisation is needed between them.
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint32_t aslot = tmem_base + 128u + (uint32_t)(((i * (kBK / 16) + k) & 15) * 8);
+                        asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(aslot), "l"(wdesc + (uint64_t)(2 * k)) : "memory");
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                            ::"r"(acc), "r"(aslot), "l"(xdesc + (uint64_t)(2 * k)), "r"(idesc), "r"((uint32_t)((i >= a.nacc) | (k != 0))));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma_bf16(acc, wdesc + (uint64_t)(2 * k), xdesc + (uint64_t)(2 * k), idesc, (uint32_t)((i >= a.nacc) | (k != 0)));
+                }
                 umma_commit(&empty[s]);
                 if (i == a.nkb - 1) umma_commit(tmem_full);
             }
@@ -361,8 +380,11 @@ int launch_gemm_dx(const GemmDx& g, cudaStream_t st, const GemmNext* next) {
     a.out_f32 = g.out_f32; a.h = (bf16*)g.h; a.ff = (bf16*)g.ff;
     a.nacc = std::max(1, std::min(std::min(lg_env_flag("LG_DX_NACC", 4), 4), a.nkb));
     while (a.nacc & (a.nacc - 1)) --a.nacc;                         // 1, 2 or 4
+    a.ts = lg_env_flag("LG_DX_TS", 0) ? 1 : 0;
+    if (a.ts && a.nacc * a.rblk > 128) a.nacc = 128 / a.rblk;     // accumulators in columns [0, 128), the A ring in [128, 256)
     a.tmem_cols = 32;
     while (a.tmem_cols < a.nacc * a.rblk) a.tmem_cols *= 2;
+    if (a.ts) a.tmem_cols = 256;
     const size_t xbytes = (size_t)a.nkb * a.rblk * 128;
     const size_t fixed = 1024 + xbytes + kMiscBytes + (norm ? (size_t)a.nkb * kBK * 2 : 0) + 64;
     int stages = (int)std::min<size_t>(kMaxSt, (227 * 1024 - fixed) / kWBytes);
