@@ -174,6 +174,12 @@ int         lg_profile_reset(void);
 int         lg_profile_read(int cls, double* total_ms, uint64_t* launches);
 const char* lg_profile_class_name(int cls);   /* NULL past the last class */
 
+/* Cap the number of CTAs (hence SMs) the VQ decoder's tensor-core convolutions occupy: ctas > 0 runs them as that many persistent
+ * CTAs, 0 restores one CTA per tile, -1 defers to the LG_CONV_CTAS environment variable (default). Process-wide; used by
+ * SamplePipeline so that decoding batch i does not evict the latency-bound AR sampling of batch i+1 from the SMs
+ * (the reference runs the two back to back, sample_c2i_ddp.py:128-143). */
+int         lg_vq_set_cta_budget(int ctas);
+
 /* ---- stand-alone kernels exported for unit parity tests ------------------------------------------- */
 /* y[M,N] (f32) = x[M,K] * w[N,K]^T, operands in `dtype`; the same dispatch the engine uses. */
 int  lg_test_gemm(const void* x, const void* w, int M, int N, int K, int dtype, float* y,

@@ -72,6 +72,7 @@ SIGNATURES = {
                              c_void_p]),
     "lg_pixels_to_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "lg_set_pdl": (c_int, [c_int]),
+    "lg_vq_set_cta_budget": (c_int, [c_int]),
     "lg_profile_enable": (c_int, [c_int]),
     "lg_profile_reset": (c_int, []),
     "lg_profile_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_uint64)]),

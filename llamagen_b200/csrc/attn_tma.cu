@@ -59,6 +59,8 @@ struct AttnTmaArgs {
     const float* freqs;
     bf16* kcache; bf16* vcache;
     unsigned long long kvhint;   // L2 eviction hint of the K/V stream (0: default policy)
+    int hd;                      // real head dim (<= HD): GPT-3B's hd = 100 runs the HD = 128 kernel over zero-padded tiles
+    int hdp;                     // elements between consecutive cache rows (112 for hd = 100: the tensor map zero-fills 112..127)
 };
 
 // FUSED = true: the kernel also IS the QKV epilogue of gpt.py:214-230 for its (row, head): it reduces the split-K
@@ -89,7 +91,8 @@ __global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
     const int grp = PAR ? warp / kWarps : 0, wk = PAR ? warp % kWarps : warp;   // ring stage owned / 16-key slice inside a chunk
     const long long row0 = a.row_base + ((long long)r * a.H + h) * a.maxS;
-    const int D = a.H * HD;
+    const int hdr = a.hd;                      // real head dim; q / slabs / out are [.., H * hdr]
+    const int D = a.H * hdr;
 
     if (threadIdx.x == 0) {
         prefetch_map(&kmap);
@@ -145,16 +148,20 @@ __global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD
         // ---- QKV epilogue for this (row, head): slab reduce -> dtype rounding -> RoPE -> cache write / smem
         if (threadIdx.x < 3 * HD / 4) {
             const int sec = threadIdx.x / (HD / 4), e = (threadIdx.x % (HD / 4)) * 4;
+            const bool live = e < hdr;                 // dims [hdr, HD) are zero padding (hdr % 4 == 0)
             const size_t N3 = (size_t)3 * D, slab = (size_t)a.R * N3;
-            const float* p = a.partial + (size_t)r * N3 + (size_t)sec * D + (size_t)h * HD + e;
-            float4 sv = *reinterpret_cast<const float4*>(p);
-            for (int k = 1; k < a.ksplit; ++k) {
-                const float4 t = *reinterpret_cast<const float4*>(p + (size_t)k * slab);
-                sv.x += t.x; sv.y += t.y; sv.z += t.z; sv.w += t.w;
+            const float* p = a.partial + (size_t)r * N3 + (size_t)sec * D + (size_t)h * hdr + e;
+            float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                sv = *reinterpret_cast<const float4*>(p);
+                for (int k = 1; k < a.ksplit; ++k) {
+                    const float4 t = *reinterpret_cast<const float4*>(p + (size_t)k * slab);
+                    sv.x += t.x; sv.y += t.y; sv.z += t.z; sv.w += t.w;
+                }
             }
             float x0 = round_bf16(sv.x), x1 = round_bf16(sv.y), x2 = round_bf16(sv.z), x3 = round_bf16(sv.w);
-            if (sec < 2) {   // apply_rotary_emb (gpt.py:420-430): adjacent pairs, fp32, separate roundings
-                const float4 cs = *reinterpret_cast<const float4*>(a.freqs + ((size_t)qpos * (HD / 2) + (e >> 1)) * 2);
+            if (sec < 2 && live) {   // apply_rotary_emb (gpt.py:420-430): adjacent pairs, fp32, separate roundings
+                const float4 cs = *reinterpret_cast<const float4*>(a.freqs + ((size_t)qpos * (hdr / 2) + (e >> 1)) * 2);
                 const float y0 = __fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y));
                 const float y1 = __fadd_rn(__fmul_rn(x1, cs.x), __fmul_rn(x0, cs.y));
                 const float y2 = __fsub_rn(__fmul_rn(x2, cs.z), __fmul_rn(x3, cs.w));
@@ -165,9 +172,9 @@ __global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD
             pk.x = pack_bf16(x0, x1);
             pk.y = pack_bf16(x2, x3);
             *reinterpret_cast<uint2*>(qbuf + sec * HD + e) = pk;
-            if (sec > 0) {
+            if (sec > 0 && live) {
                 bf16* cache = sec == 1 ? a.kcache : a.vcache;
-                *reinterpret_cast<uint2*>(cache + (((size_t)r * a.H + h) * a.maxS + qpos) * HD + e) = pk;
+                *reinterpret_cast<uint2*>(cache + (((size_t)r * a.H + h) * a.maxS + qpos) * a.hdp + e) = pk;
             }
         }
         __syncthreads();
@@ -181,13 +188,13 @@ __global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD
         }
     } else {
         // q as the A operand of m16n8k16: only MMA row 0 (lanes with g == 0) is real, the other 15 rows are zero
-        const bf16* qp = a.q + (size_t)r * D + (size_t)h * HD;
+        const bf16* qp = a.q + (size_t)r * D + (size_t)h * hdr;
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
             qa[kk][0] = 0; qa[kk][1] = 0;
             if (g == 0) {
-                qa[kk][0] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + tg * 2);
-                qa[kk][1] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + 8 + tg * 2);
+                if (kk * 16 + tg * 2 < hdr) qa[kk][0] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + tg * 2);
+                if (kk * 16 + 8 + tg * 2 < hdr) qa[kk][1] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + 8 + tg * 2);
             }
         }
     }
@@ -296,8 +303,8 @@ __global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD
         if (lane == 0) { crow[HD] = dot * a.scale; crow[HD + 1] = 1.f; }
     }
     __syncthreads();
-    bf16* op = a.out + (size_t)r * D + (size_t)h * HD;
-    for (int e = threadIdx.x; e < HD; e += blockDim.x) {
+    bf16* op = a.out + (size_t)r * D + (size_t)h * hdr;
+    for (int e = threadIdx.x; e < hdr; e += blockDim.x) {
         float M_ = -INFINITY;
 #pragma unroll
         for (int w = 0; w < NSLOT; ++w) M_ = fmaxf(M_, merge[w * (HD + 2) + HD]);
@@ -513,15 +520,17 @@ int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const CUtensorMap
 }  // namespace
 
 // KV-cache tensor maps: the whole K (or V) region of the workspace as one [rows, hd] bf16 matrix
-int attn_tma_make_map(void* map_out, const void* cache_base, long long total_rows, int hd, int tail16) {
-    return tma::make_map_2d(reinterpret_cast<CUtensorMap*>(map_out), cache_base, (uint64_t)total_rows, (uint64_t)hd, (uint64_t)hd,
+int attn_tma_make_map(void* map_out, const void* cache_base, long long total_rows, int hdp, int tail16) {
+    // hdp = cache row width in elements (64, 128, or 112 for head_dim 100: the second 64-wide box then reads 112..127 as zeros)
+    return tma::make_map_2d(reinterpret_cast<CUtensorMap*>(map_out), cache_base, (uint64_t)total_rows, (uint64_t)hdp, (uint64_t)hdp,
                             tail16 ? 16 : kKC, 64);
 }
 
 bool attn_tma_enabled() { return lg_env_flag("LG_ATTN_TMA", 1) != 0; }
 
 bool attn_tma_supported(const AttnArgs& a) {
-    return a.dtype == LG_DTYPE_BF16 && a.Tq == 1 && (a.hd == 64 || a.hd == 128) && a.kmap && a.vmap && a.kmap16 && a.vmap16 && a.R <= 65535;
+    const bool shape = a.hd == 64 || a.hd == 128 || (a.hd == 100 && a.hdp == 112);
+    return a.dtype == LG_DTYPE_BF16 && a.Tq == 1 && shape && a.kmap && a.vmap && a.kmap16 && a.vmap16 && a.R <= 65535;
 }
 
 int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
@@ -532,6 +541,7 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     t.partial = a.qkv_partial; t.ksplit = a.qkv_ksplit; t.freqs = a.freqs;
     t.kcache = (bf16*)const_cast<void*>(a.kcache); t.vcache = (bf16*)const_cast<void*>(a.vcache);
     t.kvhint = (lg_env_flag("LG_L2_HINT", 0) & 1) ? tma::kL2EvictFirst : 0ull;
+    t.hd = a.hd; t.hdp = a.hdp ? a.hdp : a.hd;
     const CUtensorMap& km = *reinterpret_cast<const CUtensorMap*>(a.kmap);
     const CUtensorMap& vm = *reinterpret_cast<const CUtensorMap*>(a.vmap);
     const CUtensorMap& km16 = *reinterpret_cast<const CUtensorMap*>(a.kmap16);
@@ -550,7 +560,7 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     // v2 (persistent warp-per-item, LG_ATTN_V2=1) measured SLOWER than the CTA-per-item kernel on B200 (25.7 vs
     // 19.1 us at R=128, c=128: with one warp per scheduler the ldmatrix->mma->softmax chain is latency-bound), so it
     // stays opt-in; profiles/ keeps both ncu captures.
-    const bool v2 = lg_env_flag("LG_ATTN_V2", 0) && a.R * a.H >= 4 * 148 && a.hd == 64 && !a.pos.rows;
+    const bool v2 = lg_env_flag("LG_ATTN_V2", 0) && a.R * a.H >= 4 * 148 && a.hd == 64 && !a.pos.rows;   // (hd 64 only)
     if (v2) return launch_v2<64>(km, vm, t, st);
     if (a.hd == 64) return launch_t<64, false>(km, vm, km16, vm16, t, st);
     return launch_t<128, false>(km, vm, km16, vm16, t, st);

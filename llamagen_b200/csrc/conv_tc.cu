@@ -42,6 +42,7 @@ struct ConvTcArgs {
     bf16* out_bf;
     float* out_nchw;
     uint8_t* out_u8;     // conv_out with the samplers' pixel finishing in the drain: uint8 NHWC [B][H][W][3] (sample_c2i_ddp.py:141-143)
+    int gx, gy, gz;      // logical tile grid (pixel patches, Cout tiles, upsample phases); the launch grid is min(gx*gy*gz, CTA budget)
 };
 
 __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap amap,
@@ -55,20 +56,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_c
     uint64_t* tmem_full_bar = empty_bar + kConvStages;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+    uint64_t* tmem_empty_bar = reinterpret_cast<uint64_t*>(tmem_base_slot + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = a.tiles_x * a.tiles_y;
-    const int b = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - b * tiles_per_img;
-    const int y0 = (trem / a.tiles_x) * a.bh, x0 = (trem % a.tiles_x) * a.bw;
-    const int n0 = blockIdx.y * a.bn;
-    const int phase = blockIdx.z, py = phase >> 1, px = phase & 1;
     const int nkb = a.ntaps * a.kchunks;
+    const int total_tiles = a.gx * a.gy * a.gz;
 
     if (warp == 0 && lane == 0) {
         prefetch_map(&amap);
         prefetch_map(&wmap);
         for (int s = 0; s < kConvStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_empty_bar, kConvThreads / 32);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_slot, (uint32_t)a.tmem_cols);
@@ -77,12 +76,26 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_c
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_slot;
 
+    // Persistent tile loop: CTA c processes tiles c, c + gridDim.x, ...  (tile = ((phase * gy) + cout_tile) * gx + pixel_patch).
+    // With gridDim.x == total_tiles this is the one-tile-per-CTA kernel; a smaller grid caps how many SMs the decoder may occupy,
+    // which is what lets the AR sampling of the next batch keep its latency while this batch is decoded (pipeline.py).
+    uint32_t it0 = 0;                      // k-blocks issued / consumed before the current tile (ring position carries across tiles)
+    uint32_t tcount = 0;                   // tiles this CTA has finished
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it0 += (uint32_t)nkb, ++tcount) {
+    const int bxi = tile % a.gx, byz = tile / a.gx;
+    const int b = bxi / tiles_per_img;
+    const int trem = bxi - b * tiles_per_img;
+    const int y0 = (trem / a.tiles_x) * a.bh, x0 = (trem % a.tiles_x) * a.bw;
+    const int n0 = (byz % a.gy) * a.bn;
+    const int phase = byz / a.gy, py = phase >> 1, px = phase & 1;
+
     if (warp == 0) {
         if (elect_one()) {
             const uint32_t tx = (uint32_t)(kATile + b_tile_bytes);
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % kConvStages;
-                const uint32_t ph = (uint32_t)((i / kConvStages) & 1);
+                const uint32_t it = it0 + (uint32_t)i;
+                const int s = (int)(it % kConvStages);
+                const uint32_t ph = (it / kConvStages) & 1u;
                 const int tap = i / a.kchunks, cc = i - tap * a.kchunks;
                 int dy = 0, dx = 0;
                 if (a.mode == 0) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
@@ -100,9 +113,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_c
         __syncwarp();
     } else if (warp == 1) {
         const uint32_t idesc = make_idesc(a.bn);
+        // the accumulator is reused: every warp must have drained the previous tile before the first MMA overwrites it
+        mbar_wait(tmem_empty_bar, (tcount & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int i = 0; i < nkb; ++i) {
-            const int s = i % kConvStages;
-            const uint32_t ph = (uint32_t)((i / kConvStages) & 1);
+            const uint32_t it = it0 + (uint32_t)i;
+            const int s = (int)(it % kConvStages);
+            const uint32_t ph = (it / kConvStages) & 1u;
             mbar_wait(&full_bar[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
@@ -129,7 +146,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_c
         if (a.mode == 2) { oy = 2 * oy + py; ox = 2 * ox + px; }
         const int cols_half = ((a.bn / 16 + 1) / 2) * 16;
         const int c_begin = half * cols_half, c_end = min(a.bn, c_begin + cols_half);
-        mbar_wait(tmem_full_bar, 0);
+        mbar_wait(tmem_full_bar, tcount & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const size_t opix = ((size_t)b * a.Hout + oy) * a.Wout + ox;
         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
@@ -188,7 +205,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_c
             reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
+        // this warp's TMEM reads of the tile are complete (tcgen05.wait::ld inside tmem_ld16): hand the accumulator back
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar);
     }
+    }   // tile loop
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
@@ -221,6 +243,9 @@ int conv_tc_make_phase_weights(const float* w_f32, bf16* out, int cout, int cin,
     LG_LAUNCH_CHECK();
     return 0;
 }
+
+static int g_conv_cta_budget = -1;      // -1: read LG_CONV_CTAS at every launch
+void conv_tc_set_cta_budget(int ctas) { g_conv_cta_budget = ctas; }
 
 bool conv_tc_supported(int Hin, int Win, int Cin, int Cout, int ksize, int up, bool nchw_out) {
     if (Cin % 64 != 0) return false;
@@ -260,13 +285,18 @@ int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16*
 
     const int b_tile_bytes = a.bn * kCk * 2;
     const int stage_bytes = kATile + ((b_tile_bytes + 1023) / 1024) * 1024;
-    const size_t smem = 1024 + (size_t)kConvStages * stage_bytes + (2 * kConvStages + 1) * sizeof(uint64_t) + 16;
+    const size_t smem = 1024 + (size_t)kConvStages * stage_bytes + (2 * kConvStages + 2) * sizeof(uint64_t) + 16;
     static DevOnce attr;
     if (lg_first_on_device(attr)) {
         LG_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     }
     LG_REQUIRE(smem <= 110 * 1024, "conv_tc: shared memory %zu too large", smem);
-    dim3 grid((unsigned)(B * a.tiles_x * a.tiles_y), (unsigned)cdiv(Cout, a.bn), up ? 4 : 1);
+    a.gx = B * a.tiles_x * a.tiles_y; a.gy = cdiv(Cout, a.bn); a.gz = up ? 4 : 1;
+    const long long total = (long long)a.gx * a.gy * a.gz;
+    LG_REQUIRE(total < (1ll << 31), "conv_tc: too many tiles");
+    // CTA budget: 0 = one CTA per tile; > 0 = persistent CTAs (lg_vq_set_cta_budget / LG_CONV_CTAS), e.g. 64 while the next batch samples
+    const int budget = g_conv_cta_budget >= 0 ? g_conv_cta_budget : lg_env_flag("LG_CONV_CTAS", 0);
+    dim3 grid((unsigned)(budget > 0 ? std::min<long long>(total, budget) : total));
     conv_tc_kernel<<<grid, kConvThreads, smem, st>>>(amap, wmap, a);
     LG_LAUNCH_CHECK();
     return 0;

@@ -130,6 +130,8 @@ struct lg_engine {
     lg_model_cfg cfg;
     int device = 0;
     int hd = 0;
+    int hdp = 0;                          // KV-cache row width in elements: hd, or 112 for head_dim 100 in bf16 (GPT-3B) so that the rows
+                                          // are 16-byte multiples and the TMA attention kernel can stream them (dims 100..111 stay zero)
     size_t esz = 2;
     std::unordered_map<std::string, Tensor> w;
     std::vector<Layer> layers;
@@ -188,7 +190,7 @@ size_t lg_engine::carve(Workspace& o, char* base, int rows, int max_seq) const {
         off += align_up(bytes);
         return p;
     };
-    o.layer_cache_bytes = (size_t)rows * H * max_seq * hd * esz;
+    o.layer_cache_bytes = (size_t)rows * H * max_seq * hdp * esz;
     o.kcache = take(o.layer_cache_bytes * L);
     o.vcache = take(o.layer_cache_bytes * L);
     o.h = take(Mmax * D * esz);
@@ -244,7 +246,7 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         AttnArgs aa;
         aa.q = ws.q; aa.kcache = ws.kcache + (size_t)l * ws.layer_cache_bytes; aa.vcache = ws.vcache + (size_t)l * ws.layer_cache_bytes;
         aa.out = ws.attn; aa.R = R; aa.Tq = Tq; aa.H = H; aa.hd = hd;
-        aa.maxS = ws.max_seq; aa.pos = pos; aa.emb_mask = emb_mask; aa.B = B;
+        aa.maxS = ws.max_seq; aa.pos = pos; aa.emb_mask = emb_mask; aa.B = B; aa.hdp = hdp;
         aa.Tc = cfg.cls_token_num; aa.scale = 1.0f / sqrtf((float)hd); aa.dtype = dt;
         if (ws.have_maps) {
             aa.kmap = ws.kmap; aa.vmap = ws.vmap; aa.kmap16 = ws.kmap16; aa.vmap16 = ws.vmap16;
@@ -307,7 +309,7 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         LG_PROF(PC_GEMM_QKV, st, gemm(ws.xn, M, 3 * D, D, ly.wqkv, nullptr, 0, &ks, nullptr, st, &nx_wo));
         QkvEpiArgs qa;
         qa.partial = ws.partial; qa.ksplit = ks; qa.M = M; qa.Tq = Tq; qa.D = D; qa.H = H; qa.hd = hd;
-        qa.pos = pos; qa.freqs = freqs; qa.q = ws.q; qa.kcache = kc; qa.vcache = vc; qa.maxS = ws.max_seq; qa.dtype = dt;
+        qa.pos = pos; qa.freqs = freqs; qa.q = ws.q; qa.kcache = kc; qa.vcache = vc; qa.maxS = ws.max_seq; qa.dtype = dt; qa.hdp = hdp;
         AttnArgs aa = attn_args(l);
         // decode steps on the TMA path: the attention kernel is also the QKV epilogue (one dependent kernel less)
         const bool fuse_qkv = lg_env_flag("LG_FUSE_QKV", 1) && attn_tma_enabled() && attn_tma_supported(aa) &&
@@ -388,6 +390,7 @@ int lg_engine_create(const lg_model_cfg* cfg, int device, lg_engine** out) {
     e->cfg = *cfg;
     e->device = device;
     e->hd = hd;
+    e->hdp = (hd == 100 && cfg->dtype == LG_DTYPE_BF16 && lg_env_flag("LG_HD_PAD", 1)) ? 112 : hd;
     e->esz = cfg->dtype == LG_DTYPE_F32 ? 4 : 2;
     const char* ng = getenv("LG_NO_GRAPH");
     e->use_graph = !(ng && ng[0] == '1');
@@ -503,13 +506,13 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
     // still be running kernels on memory the caching allocator has just recycled.
     e->ws_needs_zero = true;
     tmp.have_maps = false;
-    if (e->cfg.dtype == LG_DTYPE_BF16 && (e->hd == 64 || e->hd == 128)) {
+    if (e->cfg.dtype == LG_DTYPE_BF16 && (e->hd == 64 || e->hd == 128 || e->hdp == 112)) {
         const long long total_rows = (long long)e->cfg.n_layer * rows * e->cfg.n_head * max_seq;
         if (total_rows < (1ll << 31)) {
-            LG_TRY(attn_tma_make_map(tmp.kmap, tmp.kcache, total_rows, e->hd));
-            LG_TRY(attn_tma_make_map(tmp.vmap, tmp.vcache, total_rows, e->hd));
-            LG_TRY(attn_tma_make_map(tmp.kmap16, tmp.kcache, total_rows, e->hd, 1));
-            LG_TRY(attn_tma_make_map(tmp.vmap16, tmp.vcache, total_rows, e->hd, 1));
+            LG_TRY(attn_tma_make_map(tmp.kmap, tmp.kcache, total_rows, e->hdp));
+            LG_TRY(attn_tma_make_map(tmp.vmap, tmp.vcache, total_rows, e->hdp));
+            LG_TRY(attn_tma_make_map(tmp.kmap16, tmp.kcache, total_rows, e->hdp, 1));
+            LG_TRY(attn_tma_make_map(tmp.vmap16, tmp.vcache, total_rows, e->hdp, 1));
             tmp.have_maps = true;
         }
     }
@@ -534,7 +537,7 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
             for (int g = 0; g < n; ++g) {
                 Workspace w = tmp;
                 w.rows = hr;
-                w.layer_cache_bytes = (size_t)hr * c.n_head * max_seq * e->hd * esz;
+                w.layer_cache_bytes = (size_t)hr * c.n_head * max_seq * e->hdp * esz;
                 w.kcache = tmp.kcache + (size_t)g * w.layer_cache_bytes * c.n_layer;
                 w.vcache = tmp.vcache + (size_t)g * w.layer_cache_bytes * c.n_layer;
                 w.h = tmp.h + (size_t)g * Mh * c.dim * esz;
@@ -548,10 +551,10 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
                 w.tokens = tmp.tokens + (size_t)g * hr;
                 w.counters = tmp.counters + 2 * g;
                 const long long total_rows = (long long)c.n_layer * hr * c.n_head * max_seq;
-                LG_TRY(attn_tma_make_map(w.kmap, w.kcache, total_rows, e->hd));
-                LG_TRY(attn_tma_make_map(w.vmap, w.vcache, total_rows, e->hd));
-                LG_TRY(attn_tma_make_map(w.kmap16, w.kcache, total_rows, e->hd, 1));
-                LG_TRY(attn_tma_make_map(w.vmap16, w.vcache, total_rows, e->hd, 1));
+                LG_TRY(attn_tma_make_map(w.kmap, w.kcache, total_rows, e->hdp));
+                LG_TRY(attn_tma_make_map(w.vmap, w.vcache, total_rows, e->hdp));
+                LG_TRY(attn_tma_make_map(w.kmap16, w.kcache, total_rows, e->hdp, 1));
+                LG_TRY(attn_tma_make_map(w.vmap16, w.vcache, total_rows, e->hdp, 1));
                 w.have_maps = true;
                 e->sub[g] = w;
             }
@@ -662,8 +665,12 @@ int lg_generate(lg_engine* e, const void* cond, const float* emb_mask, int B, in
     LG_REQUIRE(e, "lg_generate: null engine");
     DeviceGuard guard(e->device);
     if (!e->works[0]) {
+        // highest priority: when the VQ decode of the previous batch runs beside the sampler (pipeline.py), a freed SM slot goes to the
+        // sampler's short dependent kernels first
+        int prio_lo = 0, prio_hi = 0;
+        LG_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         for (int i = 0; i < lg_engine::kMaxChains; ++i) {
-            LG_CUDA_OK(cudaStreamCreateWithFlags(&e->works[i], cudaStreamNonBlocking));
+            LG_CUDA_OK(cudaStreamCreateWithPriority(&e->works[i], cudaStreamNonBlocking, lg_env_flag("LG_AR_PRIORITY", 1) ? prio_hi : prio_lo));
             LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_joins[i], cudaEventDisableTiming));
         }
         LG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -821,6 +828,10 @@ static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, 
     return ret;
 }
 
+int lg_vq_set_cta_budget(int ctas) {
+    conv_tc_set_cta_budget(ctas < -1 ? -1 : ctas);
+    return 0;
+}
 int lg_set_pdl(int on) {
     g_lg_pdl = on ? 1 : 0;
     return 0;

@@ -82,6 +82,7 @@ struct QkvEpiArgs {
     void* kcache; void* vcache;         // [R, H, maxS, hd] for this layer
     int maxS;
     int dtype;
+    int hdp = 0;                        // elements between consecutive cache rows (0: hd). GPT-3B's hd = 100 is stored in 112-wide rows
 };
 int launch_qkv_epilogue(const QkvEpiArgs& a, cudaStream_t st);
 
@@ -107,6 +108,7 @@ struct AttnArgs {
     int B, Tc;
     float scale;
     int dtype;
+    int hdp = 0;            // elements between consecutive cache rows (0: hd); q / out stay [M, H*hd]
     // TMA path (attn_tma.cu): tensor maps over the whole K / V cache regions + this layer's first row
     const void* kmap = nullptr; const void* vmap = nullptr;        // kKC-row boxes
     const void* kmap16 = nullptr; const void* vmap16 = nullptr;    // 16-row boxes for the tail chunk
@@ -116,12 +118,13 @@ struct AttnArgs {
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 // attn_tma.cu — TMA + tensor-core decode attention for bf16 caches
-int attn_tma_make_map(void* map_out /*CUtensorMap, 128 B*/, const void* cache_base, long long total_rows, int hd, int tail16 = 0);
+int attn_tma_make_map(void* map_out /*CUtensorMap, 128 B*/, const void* cache_base, long long total_rows, int hdp, int tail16 = 0);
 bool attn_tma_supported(const AttnArgs& a);
 bool attn_tma_enabled();
 int launch_attention_tma(const AttnArgs& a, cudaStream_t st);
 // conv_tc.cu — tcgen05 implicit-GEMM convolution over bf16 NHWC activations (TMA 4-D boxes, TMEM accumulator)
 bool conv_tc_supported(int Hin, int Win, int Cin, int Cout, int ksize, int up, bool nchw_out);
+void conv_tc_set_cta_budget(int ctas);   // > 0: persistent conv CTAs (at most `ctas`), 0: one CTA per tile, -1: LG_CONV_CTAS
 int conv_tc_make_phase_weights(const float* w_f32, bf16* out, int cout, int cin, cudaStream_t st);
 int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16* weights, const float* bias, int Cout,
                    int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st, uint8_t* out_u8 = nullptr);

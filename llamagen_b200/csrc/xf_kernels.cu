@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(1024) qkv_epilogue_kernel(QkvEpiArgs a) {
     const int m = blockIdx.x, r = m / a.Tq, t = m % a.Tq;
     const int p = load_pos(a.pos, r) + t;
     const int D = a.D, hd = a.hd, half = hd >> 1, N = 3 * D;
+    const int hdp = a.hdp ? a.hdp : hd;                 // cache row stride
     const size_t slab = (size_t)a.M * N;
     const float* fr = a.freqs + (size_t)p * half * 2;
     T* q = reinterpret_cast<T*>(a.q);
@@ -122,14 +123,14 @@ __global__ void __launch_bounds__(1024) qkv_epilogue_kernel(QkvEpiArgs a) {
         const float x0 = TR<T>::round(sv.x), x1 = TR<T>::round(sv.y), x2 = TR<T>::round(sv.z), x3 = TR<T>::round(sv.w);
         const int sec = n / D, within = n - sec * D, head = within / hd, e = within - head * hd;   // hd % 4 == 0
         if (sec == 2) {
-            store4<T>(vc + (((size_t)r * a.H + head) * a.maxS + p) * hd + e, x0, x1, x2, x3);
+            store4<T>(vc + (((size_t)r * a.H + head) * a.maxS + p) * hdp + e, x0, x1, x2, x3);
         } else {
             const float4 cs = *reinterpret_cast<const float4*>(fr + (e >> 1) * 2);   // (cos, sin) of two pairs
             const float y0 = __fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y));
             const float y1 = __fadd_rn(__fmul_rn(x1, cs.x), __fmul_rn(x0, cs.y));
             const float y2 = __fsub_rn(__fmul_rn(x2, cs.z), __fmul_rn(x3, cs.w));
             const float y3 = __fadd_rn(__fmul_rn(x3, cs.z), __fmul_rn(x2, cs.w));
-            T* dst = sec == 0 ? q + (size_t)m * D + within : kc + (((size_t)r * a.H + head) * a.maxS + p) * hd + e;
+            T* dst = sec == 0 ? q + (size_t)m * D + within : kc + (((size_t)r * a.H + head) * a.maxS + p) * hdp + e;
             store4<T>(dst, y0, y1, y2, y3);
         }
     }
@@ -230,10 +231,11 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
     const int g = lane / LPK, li = lane - g * LPK;
     const bool active = li * VEC < HD;
     const int D = a.H * HD;
+    const int hdp = a.hdp ? a.hdp : HD;                 // cache row stride
 
     const T* qp = reinterpret_cast<const T*>(a.q) + (size_t)m * D + (size_t)h * HD;
-    const T* kbase = reinterpret_cast<const T*>(a.kcache) + ((size_t)r * a.H + h) * (size_t)a.maxS * HD;
-    const T* vbase = reinterpret_cast<const T*>(a.vcache) + ((size_t)r * a.H + h) * (size_t)a.maxS * HD;
+    const T* kbase = reinterpret_cast<const T*>(a.kcache) + ((size_t)r * a.H + h) * (size_t)a.maxS * hdp;
+    const T* vbase = reinterpret_cast<const T*>(a.vcache) + ((size_t)r * a.H + h) * (size_t)a.maxS * hdp;
     const float* mrow = a.emb_mask ? a.emb_mask + (size_t)(r % a.B) * a.Tc : nullptr;
 
     float qv[VEC];
@@ -258,8 +260,8 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) { kv[u][i] = 0.f; vv[u][i] = 0.f; }
             if (j < nkeys && active) {
-                VecLoad<T, VEC>::load(kbase + (size_t)j * HD + li * VEC, kv[u]);
-                VecLoad<T, VEC>::load(vbase + (size_t)j * HD + li * VEC, vv[u]);
+                VecLoad<T, VEC>::load(kbase + (size_t)j * hdp + li * VEC, kv[u]);
+                VecLoad<T, VEC>::load(vbase + (size_t)j * hdp + li * VEC, vv[u]);
             }
         }
 #pragma unroll

@@ -7,8 +7,11 @@ This is the steady-state loop of the reference's DDP sampler (sample_c2i_ddp.py:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
+from . import _lib
 from .generate import generate
 from .postprocess import to_uint8_nhwc
 
@@ -22,6 +25,10 @@ class SamplePipeline:
         self.dev = dev
         self.decode_stream = torch.cuda.Stream(device=dev)
         self._last = None
+        # While batch i is decoded the AR loop of batch i+1 is running: the decoder's convolutions then run as this many
+        # persistent CTAs (0 = one CTA per tile, i.e. the whole machine) so the sampler's short dependent kernels keep finding
+        # free SMs; the decode still finishes long before the sampler does (LG_PIPE_CONV_CTAS, measured in DESIGN.md section 9).
+        self.conv_ctas = int(os.environ.get("LG_PIPE_CONV_CTAS", "64"))
 
     def submit(self, cond, grid: int, to_uint8_host=None, emb_masks=None):
         """Enqueue generate() on the current stream and decode_code() on the decode stream. Returns the pixel tensor
@@ -36,6 +43,8 @@ class SamplePipeline:
         self.decode_stream.wait_event(ready)
         tokens.record_stream(self.decode_stream)
         with torch.cuda.stream(self.decode_stream):
+            if self.conv_ctas > 0:
+                _lib.load().lg_vq_set_cta_budget(self.conv_ctas)     # read at launch time by every conv of this decode
             shape = [tokens.shape[0], self.embed_dim, grid, grid]
             up = 2 ** (len(self.vq.config.decoder_ch_mult) - 1)
             if to_uint8_host is not None and tuple(to_uint8_host.shape[1:3]) == (grid * up, grid * up):
@@ -47,6 +56,8 @@ class SamplePipeline:
                 if to_uint8_host is not None:
                     u8 = to_uint8_nhwc(pixels, size=(to_uint8_host.shape[1], to_uint8_host.shape[2]))
                     to_uint8_host.copy_(u8, non_blocking=True)
+            if self.conv_ctas > 0:
+                _lib.load().lg_vq_set_cta_budget(-1)
         self._last = pixels
         return pixels
 
