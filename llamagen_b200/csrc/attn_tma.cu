@@ -69,7 +69,7 @@ struct AttnTmaArgs {
 // in EARLIER steps, so the whole KV stream is requested before the programmatic-dependency wait and overlaps the
 // QKV GEMM; one dependent kernel per layer disappears.
 template <int HD, bool FUSED, int NST, bool PAR_ = (NST > 2)>
-__global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD == 64 ? (NST > 2 ? 4 : kCtasPerSm64) : 3)) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
+__global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD == 64 ? (NST > 2 ? 4 : kCtasPerSm64) : 4)) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
                                                                const __grid_constant__ CUtensorMap vmap,
                                                                const __grid_constant__ CUtensorMap kmap16,
                                                                const __grid_constant__ CUtensorMap vmap16, AttnTmaArgs a) {

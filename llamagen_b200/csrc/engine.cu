@@ -521,7 +521,11 @@ int lg_engine_set_workspace(lg_engine* e, void* dev_ws, size_t bytes, int rows, 
     // n equal sub-batch workspaces inside the same memory (every region scales with rows, so chain g takes the g-th
     // 1/n of every region; the K/V parts stay inside the zero-initialised cache regions).
     e->n_sub = 0;
-    int n = lg_env_flag("LG_SPLIT", 2);
+    // Chain-count policy: every chain streams ALL the weights, so two chains only pay while a layer's weights survive in the 126 MB L2
+    // between the chains' visits (GPT-L 27 MB, GPT-XL 39 MB: 2 chains 292 vs 315 ms and 1 078 vs 1 174 ms per step). GPT-3B's layer is
+    // 258 MB: two chains read 12.4 GB per token instead of 6.2 (2 238 vs 1 629 ms per step, profiles/r2_s13_sweep_c4.txt) -> one chain.
+    const double layer_mb = (4.0 * e->cfg.dim * e->cfg.dim + 3.0 * e->cfg.dim * e->cfg.ffn_dim) * e->esz / 1.0e6;
+    int n = lg_env_flag("LG_SPLIT", layer_mb <= 100.0 ? 2 : 1);
     if (n > lg_engine::kMaxChains) n = lg_engine::kMaxChains;
     while (n >= 2 && (rows % n != 0 || (rows / n) % 2 != 0 || rows / n < 16)) --n;
     if (n >= 2 && e->cfg.dtype == LG_DTYPE_BF16 && tmp.have_maps) {

@@ -47,6 +47,7 @@ struct TcArgs {
     const char* pf1; unsigned long long pfb1;
     unsigned long long* trace;   // debug: [cta][8] %globaltimer stamps of the pipeline phases (nullable)
     unsigned long long whint;    // L2 eviction hint of the weight tiles (0: default policy)
+    int ld32;                    // drain with 32-column TMEM loads where possible
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -189,7 +190,21 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& map_wa, const CU
             if (threadIdx.x == 64) TC_TRACE(5);
             float* p = out + (size_t)c_begin * a.N + n;
             const size_t stride = (size_t)a.N;
-            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+            int c0 = c_begin;
+            // 32 columns per TMEM load while a full 32-row group of valid rows remains (64-row decode chains: ONE load per warp)
+            if (a.ld32) {
+                for (; c0 + 32 <= c_end && c0 + 32 <= Mb; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                    if (n < a.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { *p = __uint_as_float(v[j]); p += stride; }
+                    } else {
+                        p += 32 * stride;
+                    }
+                }
+            }
+            for (; c0 < c_end; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 if (n < a.N) {
@@ -359,6 +374,7 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
     // whole K range before the dependency wait: 3 -> 4 stages = 297.2 -> 294.9 ms/step (2 runs each), 5 no better.
     a.stages = std::min(a.stages, std::max(2, a.kblocks_per_split));   // never more stages than k-blocks
     a.trace = g_tc_trace;
+    a.ld32 = lg_env_flag("LG_TC_LD32", 1);
     a.whint = (lg_env_flag("LG_L2_HINT", 0) & 2) ? tma::kL2EvictLast : 0ull;
     const bool pf = next && lg_env_flag("LG_L2_PREFETCH", 1);
     a.pf0 = pf ? (const char*)next->p0 : nullptr; a.pfb0 = pf ? next->b0 : 0;

@@ -217,7 +217,7 @@ __global__ void reduce_f32_kernel(const float* __restrict__ partial, int ks, siz
 // contiguous head elements (128-bit loads for hd=64 bf16); every lane group runs an independent online
 // softmax over its keys; groups merge by shuffles, warps merge through shared memory.
 // Mask (gpt.py:354 + generate.py:154-163): key j visible iff j <= qpos and (j >= Tc or emb_mask[r%B, j] != 0 or j == qpos).
-template <typename T, int HD, int VEC, int LPK>
+template <typename T, int HD, int VEC, int LPK, int HDP = HD>
 __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
     lg_pdl_sync();
     constexpr int KPW = 32 / LPK;  // keys per warp per iteration
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
     const int g = lane / LPK, li = lane - g * LPK;
     const bool active = li * VEC < HD;
     const int D = a.H * HD;
-    const int hdp = a.hdp ? a.hdp : HD;                 // cache row stride
+    constexpr int hdp = HDP;                            // cache row stride (compile-time: the address math sits in the inner loop)
 
     const T* qp = reinterpret_cast<const T*>(a.q) + (size_t)m * D + (size_t)h * HD;
     const T* kbase = reinterpret_cast<const T*>(a.kcache) + ((size_t)r * a.H + h) * (size_t)a.maxS * hdp;
@@ -427,13 +427,13 @@ int launch_reduce_f32(const float* partial, int ksplit, int M, int N, float* out
     return 0;
 }
 
-template <typename T, int HD, int VEC, int LPK>
+template <typename T, int HD, int VEC, int LPK, int HDP = HD>
 static int launch_attention_t(const AttnArgs& a, cudaStream_t st) {
     const long long ctas = (long long)a.R * a.Tq * a.H;
     const int nwarps = ctas >= 592 ? 4 : 8;
     const size_t smem = (size_t)nwarps * (HD + 2) * sizeof(float);
     dim3 grid(a.H, a.R * a.Tq);
-    (void)lg_launch(attention_kernel<T, HD, VEC, LPK>, dim3(grid), dim3(nwarps * 32), smem, st, a);
+    (void)lg_launch(attention_kernel<T, HD, VEC, LPK, HDP>, dim3(grid), dim3(nwarps * 32), smem, st, a);
     LG_LAUNCH_CHECK();
     return 0;
 }
@@ -442,9 +442,11 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
     if (attn_tma_supported(a) && attn_tma_enabled()) return launch_attention_tma(a, st);
     LG_REQUIRE(a.qkv_partial == nullptr, "attention: fused QKV epilogue requested on a path that does not support it");
     LG_REQUIRE((long long)a.R * a.Tq <= 65535, "attention: too many query rows (%d x %d)", a.R, a.Tq);
+    LG_REQUIRE(a.hdp == 0 || a.hdp == a.hd || (a.hd == 100 && a.hdp == 112 && a.dtype == LG_DTYPE_BF16), "attention: unsupported KV row stride %d for head_dim %d", a.hdp, a.hd);
     if (a.dtype == LG_DTYPE_BF16) {
         if (a.hd == 64) return launch_attention_t<bf16, 64, 8, 8>(a, st);
         if (a.hd == 128) return launch_attention_t<bf16, 128, 8, 16>(a, st);
+        if (a.hd == 100 && a.hdp == 112) return launch_attention_t<bf16, 100, 4, 32, 112>(a, st);
         if (a.hd == 100) return launch_attention_t<bf16, 100, 4, 32>(a, st);
     } else if (a.dtype == LG_DTYPE_F32) {
         if (a.hd == 64) return launch_attention_t<float, 64, 8, 8>(a, st);
