@@ -519,6 +519,137 @@ int launch_t(const CUtensorMap& kmap, const CUtensorMap& vmap, const CUtensorMap
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------
+// Prefill attention for the t2i condition (Tq = T <= 128 query positions per row, gpt.py:232-236 with the causal mask of
+// gpt.py:354 and the emb_masks of generate.py:154-163): one CTA per (row, head). Q (post-RoPE, [R*T, D]) and the T freshly
+// written K/V rows arrive by TMA (one box for Q, kKC-row boxes of the cache maps for K and V), S = Q K^T and O = P V run on
+// mma.sync m16n8k16 with ldmatrix operands (each warp owns 16 query rows and skips the key blocks above its causal diagonal),
+// softmax in fp32 registers, P reused from the score fragments. Replaces one CUDA-core CTA per (query, head).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPfRows = 128;                                   // query / key rows staged per (row, head)
+constexpr int kPfBoxes = (kPfRows + kKC - 1) / kKC;            // K (or V) boxes of kKC rows
+
+__global__ void __launch_bounds__(256, 2) attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap,
+                                                                 const __grid_constant__ CUtensorMap kmap,
+                                                                 const __grid_constant__ CUtensorMap vmap, AttnTmaArgs a, int T) {
+    constexpr int HD = 64;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* qs = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // [128][64] bf16, swizzle-128B
+    uint8_t* ks = qs + kPfRows * 128;                                                              // [kPfBoxes * kKC][64]
+    uint8_t* vs = ks + kPfBoxes * kKC * 128;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(vs + kPfBoxes * kKC * 128);
+    const int h = blockIdx.x, r = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+    const long long row0 = a.row_base + ((long long)r * a.H + h) * a.maxS;
+    const int D = a.H * HD;
+    if (threadIdx.x == 0) {
+        prefetch_map(&qmap);
+        prefetch_map(&kmap);
+        prefetch_map(&vmap);
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    lg_pdl_sync();                                   // q and the K/V rows were written by the QKV epilogue just before
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (uint32_t)(kPfRows * 128 + 2 * kPfBoxes * kKC * 128));
+        load_2d(qs, &qmap, bar, h * HD, r * T);
+        for (int i = 0; i < kPfBoxes; ++i) {
+            load_2d(ks + i * kKC * 128, &kmap, bar, 0, (int)(row0 + (long long)i * kKC));
+            load_2d(vs + i * kKC * 128, &vmap, bar, 0, (int)(row0 + (long long)i * kKC));
+        }
+    }
+    mbar_wait(bar, 0);
+    const int q0 = warp * 16;                        // this warp's query rows [q0, q0 + 16)
+    if (q0 >= T) return;
+    const uint32_t qb = smem_u32(qs), kb = smem_u32(ks), vb = smem_u32(vs);
+    const int nkb = warp + 1;                        // 16-key blocks at or below the causal diagonal of these rows
+
+    float sc[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { sc[i][0] = 0.f; sc[i][1] = 0.f; sc[i][2] = 0.f; sc[i][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4(qb + swz(q0 + (lane & 15), (kk * 2 + (lane >> 4)) & 7), a0, a1, a2, a3);
+#pragma unroll
+        for (int kb16 = 0; kb16 < 8; ++kb16) {
+            if (kb16 < nkb) {
+                uint32_t b0, b1, b2, b3;
+                const int row = kb16 * 16 + (lane & 7) + ((lane >> 4) << 3);
+                ldsm_x4(kb + swz(row, (kk * 2 + ((lane >> 3) & 1)) & 7), b0, b1, b2, b3);
+                mma16816(sc[2 * kb16], a0, a1, a2, a3, b0, b1);
+                mma16816(sc[2 * kb16 + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+    }
+    // ---- mask + softmax; this thread holds rows t0 = q0 + g (values [..][0..1]) and t1 = t0 + 8 (values [..][2..3])
+    const float* mrow = a.emb_mask ? a.emb_mask + (size_t)(r % a.B) * a.Tc : nullptr;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int t = q0 + g + ((e >> 1) << 3), j = nt * 8 + tg * 2 + (e & 1);
+            bool vis = j <= t && nt < 2 * nkb;
+            if (vis && mrow && j < a.Tc && j != t) vis = mrow[j] != 0.f;
+            const float x = vis ? sc[nt][e] * a.scale : -INFINITY;
+            sc[nt][e] = x;
+            mx[e >> 1] = fmaxf(mx[e >> 1], x);
+        }
+    }
+    float l[2] = {0.f, 0.f};
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+    }
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float pv = __expf(sc[nt][e] - mx[e >> 1]);      // the diagonal key is always visible: mx is finite
+            sc[nt][e] = pv;
+            l[e >> 1] += pv;
+        }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        l[hh] += __shfl_xor_sync(0xffffffffu, l[hh], 1);
+        l[hh] += __shfl_xor_sync(0xffffffffu, l[hh], 2);
+    }
+    // ---- O = P V
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
+#pragma unroll
+    for (int kb16 = 0; kb16 < 8; ++kb16) {
+        if (kb16 < nkb) {
+            const uint32_t pa0 = pack_bf16(sc[2 * kb16][0], sc[2 * kb16][1]), pa1 = pack_bf16(sc[2 * kb16][2], sc[2 * kb16][3]);
+            const uint32_t pa2 = pack_bf16(sc[2 * kb16 + 1][0], sc[2 * kb16 + 1][1]), pa3 = pack_bf16(sc[2 * kb16 + 1][2], sc[2 * kb16 + 1][3]);
+#pragma unroll
+            for (int np = 0; np < HD / 16; ++np) {
+                uint32_t b0, b1, b2, b3;
+                const int row = kb16 * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                ldsm_x4_t(vb + swz(row, (np * 2 + (lane >> 4)) & 7), b0, b1, b2, b3);
+                mma16816(o[2 * np], pa0, pa1, pa2, pa3, b0, b1);
+                mma16816(o[2 * np + 1], pa0, pa1, pa2, pa3, b2, b3);
+            }
+        }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int t = q0 + g + hh * 8;
+        if (t < T) {
+            const float inv = 1.0f / l[hh];
+            bf16* op = a.out + ((size_t)r * T + t) * D + (size_t)h * HD;
+#pragma unroll
+            for (int i = 0; i < HD / 8; ++i)
+                *reinterpret_cast<uint32_t*>(op + i * 8 + tg * 2) = pack_bf16(o[i][2 * hh] * inv, o[i][2 * hh + 1] * inv);
+        }
+    }
+}
+
 // KV-cache tensor maps: the whole K (or V) region of the workspace as one [rows, hd] bf16 matrix
 int attn_tma_make_map(void* map_out, const void* cache_base, long long total_rows, int hdp, int tail16) {
     // hdp = cache row width in elements (64, 128, or 112 for head_dim 100: the second 64-wide box then reads 112..127 as zeros)
@@ -527,6 +658,31 @@ int attn_tma_make_map(void* map_out, const void* cache_base, long long total_row
 }
 
 bool attn_tma_enabled() { return lg_env_flag("LG_ATTN_TMA", 1) != 0; }
+
+bool attn_prefill_tc_supported(const AttnArgs& a) {
+    return a.dtype == LG_DTYPE_BF16 && a.hd == 64 && (a.hdp == 0 || a.hdp == 64) && a.Tq > 1 && a.Tq <= kPfRows && a.kmap && a.vmap &&
+           a.pos.dev == nullptr && a.pos.rows == nullptr && a.pos.value == 0 && a.R <= 65535 && a.maxS >= kPfBoxes * kKC &&
+           lg_env_flag("LG_ATTN_PREFILL_TC", 1) != 0;
+}
+
+int launch_attention_prefill_tc(const AttnArgs& a, cudaStream_t st) {
+    AttnTmaArgs t{};
+    t.q = (const bf16*)a.q; t.out = (bf16*)a.out; t.R = a.R; t.H = a.H; t.maxS = a.maxS;
+    t.row_base = a.cache_row_base; t.emb_mask = a.emb_mask; t.B = a.B; t.Tc = a.Tc; t.scale = a.scale;
+    t.hd = a.hd; t.hdp = a.hd;
+    CUtensorMap qmap;
+    LG_TRY(tma::make_map_2d(&qmap, a.q, (uint64_t)a.R * a.Tq, (uint64_t)a.H * a.hd, (uint64_t)a.H * a.hd, kPfRows, 64));
+    const size_t smem = 1024 + (size_t)kPfRows * 128 + 2 * (size_t)kPfBoxes * kKC * 128 + 16;
+    static DevOnce attr;
+    if (lg_first_on_device(attr)) {
+        LG_CUDA_OK(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    dim3 grid(a.H, a.R);
+    (void)lg_launch(attn_prefill_tc_kernel, dim3(grid), dim3(256), smem, st, qmap, *reinterpret_cast<const CUtensorMap*>(a.kmap),
+                    *reinterpret_cast<const CUtensorMap*>(a.vmap), t, a.Tq);
+    LG_LAUNCH_CHECK();
+    return 0;
+}
 
 bool attn_tma_supported(const AttnArgs& a) {
     const bool shape = a.hd == 64 || a.hd == 128 || (a.hd == 100 && a.hdp == 112);

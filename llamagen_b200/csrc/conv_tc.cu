@@ -216,6 +216,176 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_c
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Weights-as-A variant for Cout % 128 == 0 (every ResnetBlock / Upsample / Downsample conv of the VQ models).
+//
+// Why: in the SS form a tcgen05.mma with M = 128 costs ~170 cycles whatever N is (the A operand is fetched at about one row per
+// cycle), so the kernel above (A = 128 pixels, N = Cout tile <= 128) tops out at 128*128*16*2 flop / 170 cycles =
+// 867 TFLOP/s on 148 SMs - exactly what it measures (873). Here A = the 128-row weight slab and B = a 16x16-pixel patch (two 4-D
+// TMA boxes = 256 pixels), so every instruction does twice the work: N = 256, the UMMA maximum.
+//
+// TMEM holds the tile as [lane = output channel][column = pixel]. The drain goes through shared memory 64 pixels at a time
+// (fp32 [64][128] in a retired B stage) so that global traffic stays 16-byte vectors along the NHWC channel axis and
+// acc + bias + residual is rounded to bf16 once, as in the kernel above.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kWStages = 2;                      // 2 x 48 KB: two CTAs per SM overlap one tile's drain with the other's MMAs
+constexpr int kWATile = 128 * kCk * 2;           // weights: 128 couts x 64 ch = 16 KB
+constexpr int kWBTile = 256 * kCk * 2;           // pixels: 256 x 64 ch = 32 KB (two 8x16 boxes)
+constexpr int kWStage = kWATile + kWBTile;
+
+__global__ void __launch_bounds__(kConvThreads, 2) conv_tcw_kernel(const __grid_constant__ CUtensorMap amap,
+                                                                   const __grid_constant__ CUtensorMap wmap, ConvTcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kWStages * kWStage);
+    uint64_t* empty_bar = full_bar + kWStages;
+    uint64_t* tmem_full_bar = empty_bar + kWStages;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_empty_bar = reinterpret_cast<uint64_t*>(tmem_base_slot + 2);
+    float* bias_s = reinterpret_cast<float*>(tmem_empty_bar + 1);     // [128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int nkb = a.ntaps * a.kchunks;
+    const int total_tiles = a.gx * a.gy * a.gz;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_map(&amap);
+        prefetch_map(&wmap);
+        for (int s = 0; s < kWStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_empty_bar, kConvThreads / 32);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_slot, 256u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    uint32_t it0 = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it0 += (uint32_t)nkb, ++tcount) {
+        const int bxi = tile % a.gx, byz = tile / a.gx;
+        const int b = bxi / tiles_per_img;
+        const int trem = bxi - b * tiles_per_img;
+        const int y0 = (trem / a.tiles_x) * 16, x0 = (trem % a.tiles_x) * 16;      // 16x16-pixel patch
+        const int n0 = (byz % a.gy) * 128;
+        const int phase = byz / a.gy, py = phase >> 1, px = phase & 1;
+
+        if (warp == 0) {
+            if (elect_one()) {
+                for (int i = 0; i < nkb; ++i) {
+                    const uint32_t it = it0 + (uint32_t)i;
+                    const int s = (int)(it % kWStages);
+                    const uint32_t ph = (it / kWStages) & 1u;
+                    const int tap = i / a.kchunks, cc = i - tap * a.kchunks;
+                    int dy = 0, dx = 0, ys = 8;
+                    if (a.mode == 0) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                    else if (a.mode == 2) { const int ta = tap >> 1, tb = tap & 1; dy = py == 0 ? ta - 1 : ta; dx = px == 0 ? tb - 1 : tb; }
+                    else if (a.mode == 3) { dy = y0 + tap / 3; dx = x0 + tap % 3; ys = 16; }   // stride-2 map: coordinates are input pixels
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], (uint32_t)kWStage);
+                    uint8_t* sa = tiles + s * kWStage;
+                    load_2d(sa, &wmap, &full_bar[s], tap * a.Cin + cc * kCk, phase * a.Cout + n0);
+                    load_4d(sa + kWATile, &amap, &full_bar[s], cc * kCk, x0 + dx, y0 + dy, b);
+                    load_4d(sa + kWATile + kWBTile / 2, &amap, &full_bar[s], cc * kCk, x0 + dx, y0 + dy + ys, b);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            const uint32_t idesc = make_idesc(256);
+            mbar_wait(tmem_empty_bar, (tcount & 1u) ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int i = 0; i < nkb; ++i) {
+                const uint32_t it = it0 + (uint32_t)i;
+                const int s = (int)(it % kWStages);
+                const uint32_t ph = (it / kWStages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(tiles + s * kWStage);
+                    const uint64_t adesc = make_desc_sw128(sa);
+                    const uint64_t bdesc = make_desc_sw128(sa + kWATile);
+#pragma unroll
+                    for (int k = 0; k < kCk / 16; ++k)
+                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
+                    // the last two k-blocks do not release their stages through the ring: the drain reuses stage memory, so the
+                    // producer may only refill after every warp has left the drain (tmem_empty)
+                    if (i < nkb - kWStages) umma_commit(&empty_bar[s]);
+                    if (i == nkb - 1) umma_commit(tmem_full_bar);
+                }
+                __syncwarp();
+            }
+        }
+        if (threadIdx.x >= 64 && threadIdx.x < 192) bias_s[threadIdx.x - 64] = n0 + (int)threadIdx.x - 64 < a.Cout ? a.bias[n0 + threadIdx.x - 64] : 0.f;
+
+        // ------------------------------------------------------------------ drain: 4 rounds of 64 pixels through shared memory
+        mbar_wait(tmem_full_bar, tcount & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // every MMA has retired (tmem_full), so all stage memory is idle: staging buffer = the B half of stage 0
+        float* stg = reinterpret_cast<float*>(tiles + kWATile);            // [64 pixels][128 channels] fp32 = 32 KB
+        const int q = warp & 3, half = warp >> 2;
+        const int ch = q * 32 + lane;                                      // output channel inside the tile = TMEM lane
+        for (int rnd = 0; rnd < 4; ++rnd) {
+            // TMEM -> staging: this warp takes 32 of the round's 64 pixel columns
+            {
+                const int c0 = rnd * 64 + half * 32;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[(half * 32 + j) * 128 + ch] = __uint_as_float(v[j]);
+            }
+            __syncthreads();
+            // staging -> global: 64 pixels x 16 chunks of 8 channels; thread -> 4 chunks
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = u * kConvThreads + (int)threadIdx.x;      // [0, 1024)
+                const int pl = idx >> 4, c8 = (idx & 15) * 8;             // pixel inside the round, first of 8 channels
+                const int n = rnd * 64 + pl;                               // pixel column of the tile: box = n / 128, row-major 8x16 inside
+                const int iy = (n >> 7) * 8 + ((n & 127) >> 4), ix = n & 15;
+                int oy = y0 + iy, ox = x0 + ix;
+                if (oy >= a.Ht || ox >= a.Wt) continue;                   // the patch may overhang the image
+                if (a.mode == 2) { oy = 2 * oy + py; ox = 2 * ox + px; }
+                const size_t off = (((size_t)b * a.Hout + oy) * a.Wout + ox) * a.Cout + n0 + c8;
+                const float4 f0 = *reinterpret_cast<const float4*>(stg + pl * 128 + c8);
+                const float4 f1 = *reinterpret_cast<const float4*>(stg + pl * 128 + c8 + 4);
+                float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += bias_s[c8 + j];
+                if (a.residual) {
+                    const uint4 r = *reinterpret_cast<const uint4*>(a.residual + off);
+                    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        f[2 * j] += __uint_as_float(w[j] << 16);
+                        f[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+                    }
+                }
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                    pk[j] = *reinterpret_cast<uint32_t*>(&t);
+                }
+                *reinterpret_cast<uint4*>(a.out_bf + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            __syncthreads();
+        }
+        // hand the accumulator AND the stage memory back: the MMA warp waits on tmem_empty before the next tile's first MMA, the
+        // producer on the two stage-empty barriers released here
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar);
+        if (threadIdx.x == 0) {
+            const int nrel = nkb < kWStages ? nkb : kWStages;
+            for (int i = nkb - nrel; i < nkb; ++i) mbar_arrive(&empty_bar[(it0 + (uint32_t)i) % kWStages]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 256u);
+}
+
 // W'[phase][co][a*2+b][ci] = sum of the 3x3 taps that land on input offset (a, b) for output parity (py, px)
 __global__ void upsample_phase_weights_kernel(const float* __restrict__ w /*[Cout][Cin][3][3]*/, bf16* __restrict__ out,
                                               int cout, int cin) {
@@ -291,11 +461,35 @@ int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16*
         LG_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     }
     LG_REQUIRE(smem <= 110 * 1024, "conv_tc: shared memory %zu too large", smem);
+    // CTA budget: 0 = one CTA per tile; > 0 = persistent CTAs (lg_vq_set_cta_budget / LG_CONV_CTAS), e.g. 64 while the next batch samples
+    const int budget = g_conv_cta_budget >= 0 ? g_conv_cta_budget : lg_env_flag("LG_CONV_CTAS", 0);
+    if (Cout % 128 == 0 && a.Ht >= 16 && a.Wt >= 16 && out_bf && !out_nchw && !out_u8 && lg_env_flag("LG_CONV_SWAP", 1)) {
+        // weights-as-A kernel: 128 couts x a 16x16-pixel patch (two 8x16 boxes) per tile
+        ConvTcArgs w = a;
+        w.bw = 16; w.bh = 8;
+        w.tiles_x = cdiv(a.Wt, 16); w.tiles_y = cdiv(a.Ht, 16);
+        w.bn = 128;
+        w.gx = B * w.tiles_x * w.tiles_y; w.gy = Cout / 128; w.gz = up ? 4 : 1;
+        CUtensorMap amap2, wmap2;
+        LG_TRY(tma::make_map_nhwc(&amap2, in, (uint64_t)B, (uint64_t)Hin, (uint64_t)Win, (uint64_t)Cin, 8u, 16u, kCk, down ? 2u : 1u));
+        const uint64_t wrows2 = (uint64_t)(up ? 4 : 1) * Cout, wcols2 = (uint64_t)a.ntaps * Cin;
+        LG_TRY(tma::make_map_2d(&wmap2, weights, wrows2, wcols2, wcols2, 128u, kCk));
+        const size_t smem2 = 1024 + (size_t)kWStages * kWStage + (2 * kWStages + 2) * sizeof(uint64_t) + 16 + 128 * sizeof(float);
+        static DevOnce attr2;
+        if (lg_first_on_device(attr2)) {
+            LG_CUDA_OK(cudaFuncSetAttribute(conv_tcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        }
+        LG_REQUIRE(smem2 <= 110 * 1024, "conv_tcw: shared memory %zu too large", smem2);
+        const long long total2 = (long long)w.gx * w.gy * w.gz;
+        LG_REQUIRE(total2 < (1ll << 31), "conv_tcw: too many tiles");
+        dim3 grid2((unsigned)(budget > 0 ? std::min<long long>(total2, budget) : total2));
+        conv_tcw_kernel<<<grid2, kConvThreads, smem2, st>>>(amap2, wmap2, w);
+        LG_LAUNCH_CHECK();
+        return 0;
+    }
     a.gx = B * a.tiles_x * a.tiles_y; a.gy = cdiv(Cout, a.bn); a.gz = up ? 4 : 1;
     const long long total = (long long)a.gx * a.gy * a.gz;
     LG_REQUIRE(total < (1ll << 31), "conv_tc: too many tiles");
-    // CTA budget: 0 = one CTA per tile; > 0 = persistent CTAs (lg_vq_set_cta_budget / LG_CONV_CTAS), e.g. 64 while the next batch samples
-    const int budget = g_conv_cta_budget >= 0 ? g_conv_cta_budget : lg_env_flag("LG_CONV_CTAS", 0);
     dim3 grid((unsigned)(budget > 0 ? std::min<long long>(total, budget) : total));
     conv_tc_kernel<<<grid, kConvThreads, smem, st>>>(amap, wmap, a);
     LG_LAUNCH_CHECK();

@@ -122,6 +122,9 @@ int attn_tma_make_map(void* map_out /*CUtensorMap, 128 B*/, const void* cache_ba
 bool attn_tma_supported(const AttnArgs& a);
 bool attn_tma_enabled();
 int launch_attention_tma(const AttnArgs& a, cudaStream_t st);
+// t2i condition prefill (1 < Tq <= 128, hd 64, bf16): TMA-staged Q/K/V, mma.sync QK^T and PV, one CTA per (row, head)
+bool attn_prefill_tc_supported(const AttnArgs& a);
+int launch_attention_prefill_tc(const AttnArgs& a, cudaStream_t st);
 // conv_tc.cu — tcgen05 implicit-GEMM convolution over bf16 NHWC activations (TMA 4-D boxes, TMEM accumulator)
 bool conv_tc_supported(int Hin, int Win, int Cin, int Cout, int ksize, int up, bool nchw_out);
 void conv_tc_set_cta_budget(int ctas);   // > 0: persistent conv CTAs (at most `ctas`), 0: one CTA per tile, -1: LG_CONV_CTAS

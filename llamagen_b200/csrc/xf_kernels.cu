@@ -440,6 +440,7 @@ static int launch_attention_t(const AttnArgs& a, cudaStream_t st) {
 
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
     if (attn_tma_supported(a) && attn_tma_enabled()) return launch_attention_tma(a, st);
+    if (attn_prefill_tc_supported(a) && attn_tma_enabled() && a.qkv_partial == nullptr) return launch_attention_prefill_tc(a, st);
     LG_REQUIRE(a.qkv_partial == nullptr, "attention: fused QKV epilogue requested on a path that does not support it");
     LG_REQUIRE((long long)a.R * a.Tq <= 65535, "attention: too many query rows (%d x %d)", a.R, a.Tq);
     LG_REQUIRE(a.hdp == 0 || a.hdp == a.hd || (a.hd == 100 && a.hdp == 112 && a.dtype == LG_DTYPE_BF16), "attention: unsupported KV row stride %d for head_dim %d", a.hdp, a.hd);

@@ -304,6 +304,34 @@ def test_small_row_path_t2i_masked_condition(monkeypatch):
 
 
 
+@pytest.mark.parametrize("B", [2, 12])
+def test_t2i_prefill_tensor_core_attention(B, monkeypatch):
+    """The T = 120 condition prefill runs its masked causal attention on the TMA + mma.sync kernel (attn_prefill_tc_kernel, one
+    CTA per (row, head)); the CUDA-core kernel (one CTA per query) is the reference point, with ragged left-padded emb_masks
+    (generate.py:154-163) and CFG twin rows. The prefill logits feed token 0, the cache feeds every later step."""
+    from llamagen_b200.gpt import ModelArgs, Transformer
+    torch.manual_seed(11)
+    m = Transformer(ModelArgs(n_layer=3, n_head=4, dim=256, block_size=64, vocab_size=1024, cls_token_num=120, caption_dim=64,
+                              model_type="t2i"))
+    m.output.weight.data.normal_(std=0.02)
+    m = m.to(device="cuda", dtype=torch.bfloat16).eval()
+    S = 24
+    em = torch.zeros(B, 120)
+    for b in range(B):
+        em[b, -(1 + (37 * b + 5) % 120):] = 1                   # left-padded: valid tokens at the right end, 6..120 of them
+    cond = (torch.randn(B, 120, 64) * em[:, :, None]).bfloat16()
+    teacher = torch.randint(0, 1024, (B, S), generator=torch.Generator().manual_seed(6), dtype=torch.int32)
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("LG_ATTN_PREFILL_TC", flag)
+        _, outs[flag] = _gen(m, cond, S, em, cfg_scale=3.0, teacher=teacher.clone())
+    err = (outs["1"] - outs["0"]).abs()
+    scale = outs["0"].std().item()
+    assert err.max().item() <= 0.2 * scale + 0.05, (err.max().item(), scale)
+    assert err.mean().item() <= 0.03 * scale + 0.005, (err.mean().item(), scale)
+    assert err[0].max().item() <= 0.2 * scale + 0.05            # step 0 = the prefill's own logits
+
+
 @pytest.mark.parametrize("model,B", [("GPT-B", 1), ("GPT-B", 4), ("GPT-L", 1)])
 def test_persistent_decode_kernel_vs_oracle(model, B, monkeypatch):
     """LG_PERSIST=1: R <= 8 decode steps run as ONE cooperative persistent kernel per token (decode_persist.cu: grid barriers between
