@@ -140,6 +140,12 @@ __global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD
     if (threadIdx.x == 0)
         for (int ci = 0; ci < npro; ++ci)
             if (FUSED || ci != nchunks - 1) issue(ci);
+    // RoPE angles of this step's position: a table lookup that does not depend on the producer kernel -> issued before the wait
+    float4 cs_pre = make_float4(1.f, 0.f, 1.f, 0.f);
+    if (FUSED && threadIdx.x < 2 * HD / 4) {
+        const int e = (threadIdx.x % (HD / 4)) * 4;
+        if (e < hdr) cs_pre = __ldg(reinterpret_cast<const float4*>(a.freqs + ((size_t)qpos * (hdr / 2) + (e >> 1)) * 2));
+    }
     lg_pdl_sync();
     if (!FUSED && threadIdx.x == 0 && nchunks - 1 < npro && nchunks > 0) issue(nchunks - 1);
 
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD
             }
             float x0 = round_bf16(sv.x), x1 = round_bf16(sv.y), x2 = round_bf16(sv.z), x3 = round_bf16(sv.w);
             if (sec < 2 && live) {   // apply_rotary_emb (gpt.py:420-430): adjacent pairs, fp32, separate roundings
-                const float4 cs = *reinterpret_cast<const float4*>(a.freqs + ((size_t)qpos * (hdr / 2) + (e >> 1)) * 2);
+                const float4 cs = cs_pre;
                 const float y0 = __fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y));
                 const float y1 = __fadd_rn(__fmul_rn(x1, cs.x), __fmul_rn(x0, cs.y));
                 const float y2 = __fsub_rn(__fmul_rn(x2, cs.z), __fmul_rn(x3, cs.w));
@@ -696,7 +702,7 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     t.emb_mask = a.emb_mask; t.B = a.B; t.Tc = a.Tc; t.scale = a.scale;
     t.partial = a.qkv_partial; t.ksplit = a.qkv_ksplit; t.freqs = a.freqs;
     t.kcache = (bf16*)const_cast<void*>(a.kcache); t.vcache = (bf16*)const_cast<void*>(a.vcache);
-    t.kvhint = (lg_env_flag("LG_L2_HINT", 0) & 1) ? tma::kL2EvictFirst : 0ull;
+    t.kvhint = (lg_env_flag("LG_L2_HINT", 1) & 1) ? tma::kL2EvictFirst : 0ull;
     t.hd = a.hd; t.hdp = a.hdp ? a.hdp : a.hd;
     const CUtensorMap& km = *reinterpret_cast<const CUtensorMap*>(a.kmap);
     const CUtensorMap& vm = *reinterpret_cast<const CUtensorMap*>(a.vmap);

@@ -43,6 +43,9 @@ struct ConvTcArgs {
     float* out_nchw;
     uint8_t* out_u8;     // conv_out with the samplers' pixel finishing in the drain: uint8 NHWC [B][H][W][3] (sample_c2i_ddp.py:141-143)
     int gx, gy, gz;      // logical tile grid (pixel patches, Cout tiles, upsample phases); the launch grid is min(gx*gy*gz, CTA budget)
+    float* gn_partial;   // conv_tcw_kernel: per (image, tile, group) sum / sum of squares of the bf16 OUTPUT for the following
+    int gn_cpg;          // GroupNorm(32) (vq_model.py:279-314): [B][gn_splits][32][2], channels per group, tiles per image
+    int gn_splits;
 };
 
 __global__ void __launch_bounds__(kConvThreads, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap amap,
@@ -326,6 +329,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tcw_kernel(const __grid_
         float* stg = reinterpret_cast<float*>(tiles + kWATile);            // [64 pixels][128 channels] fp32 = 32 KB
         const int q = warp & 3, half = warp >> 2;
         const int ch = q * 32 + lane;                                      // output channel inside the tile = TMEM lane
+        float gs[8], gq[8];                                                // GroupNorm statistics of this thread's 8 channels
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gs[j] = 0.f; gq[j] = 0.f; }
         for (int rnd = 0; rnd < 4; ++rnd) {
             // TMEM -> staging: this warp takes 32 of the round's 64 pixel columns
             {
@@ -368,6 +374,35 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_tcw_kernel(const __grid_
                     pk[j] = *reinterpret_cast<uint32_t*>(&t);
                 }
                 *reinterpret_cast<uint4*>(a.out_bf + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (a.gn_partial) {          // statistics of the values as stored (bf16), like gn_stats_kernel reading them back
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float lo = __uint_as_float(pk[j] << 16), hi = __uint_as_float(pk[j] & 0xffff0000u);
+                        gs[2 * j] += lo; gq[2 * j] = fmaf(lo, lo, gq[2 * j]);
+                        gs[2 * j + 1] += hi; gq[2 * j + 1] = fmaf(hi, hi, gq[2 * j + 1]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (a.gn_partial) {
+            // thread t owns channels (t & 15) * 8 .. +7 of the tile for 16 of its pixels: combine the 16 threads of a channel column
+            // and the channels of a group in a fixed order (no atomics: decode_code stays bit-reproducible)
+            float* part = stg;                                             // [256 threads][16]
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { part[threadIdx.x * 16 + j] = gs[j]; part[threadIdx.x * 16 + 8 + j] = gq[j]; }
+            __syncthreads();
+            const int ngrp = 128 / a.gn_cpg;
+            if ((int)threadIdx.x < ngrp) {
+                float ts = 0.f, tq = 0.f;
+                for (int c = (int)threadIdx.x * a.gn_cpg; c < ((int)threadIdx.x + 1) * a.gn_cpg; ++c) {
+                    const int col = c >> 3, ci = c & 7;
+                    for (int j = 0; j < 16; ++j) { ts += part[(col + 16 * j) * 16 + ci]; tq += part[(col + 16 * j) * 16 + 8 + ci]; }
+                }
+                const int split = phase * tiles_per_img + trem;
+                float* o = a.gn_partial + (((size_t)b * a.gn_splits + split) * 32 + (n0 / a.gn_cpg + (int)threadIdx.x)) * 2;
+                o[0] = ts;
+                o[1] = tq;
             }
             __syncthreads();
         }
@@ -428,8 +463,11 @@ bool conv_tc_supported(int Hin, int Win, int Cin, int Cout, int ksize, int up, b
 
 // weights: up == 0 or 2 (stride-2 Downsample) -> [Cout][k*k][Cin] bf16 ; up == 1 -> phase weights [4][Cout][4][Cin] bf16
 int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16* weights, const float* bias, int Cout,
-                   int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st, uint8_t* out_u8) {
+                   int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st, uint8_t* out_u8,
+                   float* gn_partial, size_t gn_floats, int* gn_splits) {
+    if (gn_splits) *gn_splits = 0;
     ConvTcArgs a;
+    a.gn_partial = nullptr; a.gn_cpg = 0; a.gn_splits = 0;
     a.B = B; a.Hin = Hin; a.Win = Win; a.Cin = Cin; a.Cout = Cout;
     const bool down = up == 2;
     up = up == 1;
@@ -470,6 +508,12 @@ int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16*
         w.tiles_x = cdiv(a.Wt, 16); w.tiles_y = cdiv(a.Ht, 16);
         w.bn = 128;
         w.gx = B * w.tiles_x * w.tiles_y; w.gy = Cout / 128; w.gz = up ? 4 : 1;
+        // GroupNorm(32) statistics of the output in the drain: every (image, tile, group) slot is written by exactly one CTA
+        const int splits = w.tiles_x * w.tiles_y * w.gz, cpg = Cout / 32;
+        if (gn_partial && gn_splits && Cout % 32 == 0 && 128 % cpg == 0 && (size_t)B * splits * 64 <= gn_floats && lg_env_flag("LG_GN_FUSE", 1)) {
+            w.gn_partial = gn_partial; w.gn_cpg = cpg; w.gn_splits = splits;
+            *gn_splits = splits;
+        }
         CUtensorMap amap2, wmap2;
         LG_TRY(tma::make_map_nhwc(&amap2, in, (uint64_t)B, (uint64_t)Hin, (uint64_t)Win, (uint64_t)Cin, 8u, 16u, kCk, down ? 2u : 1u));
         const uint64_t wrows2 = (uint64_t)(up ? 4 : 1) * Cout, wcols2 = (uint64_t)a.ntaps * Cin;

@@ -148,6 +148,7 @@ struct lg_engine {
     const int32_t* pd_tokens = nullptr;   // set by the caller of forward() when the step's token ids are in device memory and the
                                           // embedding lookup has NOT been launched (the persistent kernel gathers the rows itself)
     bool ws_needs_zero = false;           // KV cache + counters of `full` still have to be zero-filled (done on the caller's stream)
+    bool skip_first_norm = false;         // set by the decode loop when the sample kernel's fused tail already wrote xn = RMSNorm_0(h)
     cudaStream_t works[kMaxChains] = {};   // engine-owned streams (one per chain)
     cudaEvent_t ev_fork = nullptr, ev_joins[kMaxChains] = {};
     ~lg_engine() {
@@ -165,6 +166,13 @@ struct lg_engine {
                decode_persist_part_floats(R, cfg.n_head, hd) <= ws.partial_floats;
     }
 
+    // R <= 8 decode steps on the column-owner GEMV path (gemv_small.cu); shared by forward() and the decode loop's fused tail
+    bool small_row_path(int M, const AttnArgs& aa) const {
+        const int D = cfg.dim, F = cfg.ffn_dim, V = cfg.vocab_size, dt = cfg.dtype;
+        return M <= 8 && lg_env_flag("LG_SMALL_R", 1) && lg_env_flag("LG_FUSE_QKV", 1) && attn_tma_enabled() && attn_tma_supported(aa) &&
+               gemv_small_supported(M, 3 * D, D, dt, false) && gemv_small_supported(M, D, D, dt, false) &&
+               gemv_small_supported(M, F, D, dt, true) && gemv_small_supported(M, D, F, dt, false) && gemv_small_supported(M, V, D, dt, false);
+    }
     size_t carve(Workspace& o, char* base, int rows, int max_seq) const;
     int zero_fill_if_needed(cudaStream_t st) {
         if (!ws_needs_zero || !full.base) return 0;
@@ -270,9 +278,8 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         return 0;
     }
     // ---- R <= 8 decode step (batch-1 latency path, gemv_small.cu): 5 dependent kernels per layer, no slabs
-    if (Tq == 1 && M <= 8 && lg_env_flag("LG_SMALL_R", 1) && lg_env_flag("LG_FUSE_QKV", 1) && attn_tma_enabled() &&
-        attn_tma_supported(attn_args(0)) && gemv_small_supported(M, 3 * D, D, dt, false) && gemv_small_supported(M, D, D, dt, false) &&
-        gemv_small_supported(M, F, D, dt, true) && gemv_small_supported(M, D, F, dt, false) && gemv_small_supported(M, V, D, dt, false)) {
+    if (Tq == 1 && small_row_path(M, attn_args(0))) {
+        skip_first_norm = false;
         for (int l = 0; l < L; ++l) {
             const Layer& ly = layers[l];
             GemvSmall gq{ly.wqkv, nullptr, 3 * D, D, M, ws.h, ly.attn_norm, cfg.norm_eps, ws.partial, nullptr, nullptr};
@@ -291,7 +298,8 @@ int lg_engine::forward(int M, int Tq, PosArg pos, const float* emb_mask, int B, 
         LG_PROF(PC_GEMM_HEAD, st, launch_gemv_small(gh, st));
         return 0;
     }
-    LG_PROF(PC_EMBED_MISC, st, launch_rmsnorm(ws.h, layers[0].attn_norm, ws.xn, M, D, cfg.norm_eps, dt, st));
+    if (!skip_first_norm) LG_PROF(PC_EMBED_MISC, st, launch_rmsnorm(ws.h, layers[0].attn_norm, ws.xn, M, D, cfg.norm_eps, dt, st));
+    skip_first_norm = false;
     // Direct-epilogue GEMMs (gemm_dx.cu, 6 kernels per layer instead of 8) are validated but OFF by default: a CTA that owns the full
     // reduction issues 64 dependent tcgen05.mma steps (~0.37 us per 64-wide k-block whatever the UMMA N, measured), so each of the
     // two kernels costs 10-13 us against 4.4 + 3.2 us for the split-K GEMM + row kernel it replaces (392 vs 292 ms/step).
@@ -746,15 +754,42 @@ static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, 
         sa.dbg_logits = dbg_logits; sa.dbg_batch = B;
     }
 
+    // Fused tail (bf16): the sample kernel writes the next step's input rows (token embedding, and on the batched path the layer-0
+    // RMSNorm) and advances the device-resident counters, so a decode iteration loses its embed / rmsnorm / advance kernels.
+    const bool fuse_tail = c.dtype == LG_DTYPE_BF16 && lg_env_flag("LG_FUSE_TAIL", 1) && c.dim % 2 == 0;
+    auto tail_on = [&](Chain& k) -> bool {
+        e->ws = k.w;
+        return fuse_tail && !e->persist_usable(k.R);
+    };
+    auto arm_tail = [&](Chain& k, bool advance) {
+        SampleArgs& sa = k.sa;
+        e->ws = k.w;
+        AttnArgs aa{};
+        aa.R = k.R; aa.Tq = 1; aa.H = c.n_head; aa.hd = e->hd; aa.hdp = e->hdp; aa.dtype = c.dtype;
+        if (k.w.have_maps) { aa.kmap = k.w.kmap; aa.vmap = k.w.vmap; aa.kmap16 = k.w.kmap16; aa.vmap16 = k.w.vmap16; }
+        const bool small = e->small_row_path(k.R, aa);
+        sa.emb_table = e->tok_emb; sa.emb_h = k.w.h; sa.emb_D = c.dim; sa.emb_rows = k.R;
+        sa.emb_xn = small ? nullptr : k.w.xn;
+        sa.emb_norm_w = e->layers[0].attn_norm; sa.emb_eps = c.norm_eps;
+        sa.adv_pos = advance ? k.w.counters : nullptr;
+        sa.adv_step = advance ? k.w.counters + 1 : nullptr;
+        sa.adv_ticket = advance ? reinterpret_cast<unsigned int*>(k.w.counters + 64) : nullptr;
+    };
     auto body = [&](Chain& k) -> int {
         e->ws = k.w;
         int* d_pos = k.w.counters;
         int* d_step = k.w.counters + 1;
-        if (e->persist_usable(k.R)) e->pd_tokens = k.w.tokens;
-        else LG_PROF(PC_EMBED_MISC, k.st, launch_embed(e->tok_emb, k.w.tokens, k.B, k.R, -1, c.dim, c.dtype, k.w.h, k.st));
+        const bool tail = tail_on(k);
+        if (tail) {
+            e->skip_first_norm = k.sa.emb_xn != nullptr;     // the previous iteration's sample kernel left h (and xn) in place
+        } else if (e->persist_usable(k.R)) {
+            e->pd_tokens = k.w.tokens;
+        } else {
+            LG_PROF(PC_EMBED_MISC, k.st, launch_embed(e->tok_emb, k.w.tokens, k.B, k.R, -1, c.dim, c.dtype, k.w.h, k.st));
+        }
         LG_TRY(e->forward(k.R, 1, PosArg{d_pos, 0}, k.emb_mask, k.B, k.w.logits, false, k.st));
         LG_PROF(PC_SAMPLE, k.st, launch_sample(k.sa, k.st));
-        LG_PROF(PC_EMBED_MISC, k.st, launch_advance(d_pos, d_step, k.st));
+        if (!tail) LG_PROF(PC_EMBED_MISC, k.st, launch_advance(d_pos, d_step, k.st));
         return 0;
     };
 
@@ -765,10 +800,13 @@ static int generate_impl(lg_engine* e, const void* cond, const float* emb_mask, 
         LG_TRY(e->embed_cond(k.cond, k.B, k.R, T, k.st));
         LG_TRY(e->forward(k.R * T, T, PosArg{nullptr, 0}, k.emb_mask, k.B, k.w.logits, false, k.st));
         k.sa.step = 0; k.sa.step_dev = nullptr;
+        const bool tail = S > 1 && tail_on(k);
+        if (tail) arm_tail(k, false);            // the prefill's sample prepares the first decode step's rows; counters are set below
         LG_TRY(launch_sample(k.sa, k.st));
         if (S == 1) continue;
         LG_TRY(launch_set_counters(k.w.counters, T, k.w.counters + 1, 1, k.st));
         k.sa.step_dev = k.w.counters + 1;
+        if (tail) arm_tail(k, true);
         LG_TRY(body(k));   // first decode step runs eagerly (also sets every kernel attribute outside capture)
     }
     const int remaining = S - 2;

@@ -375,7 +375,7 @@ static int gemm_tc_launch(const void* X, int ldx, const void* Wa, const void* Wb
     a.stages = std::min(a.stages, std::max(2, a.kblocks_per_split));   // never more stages than k-blocks
     a.trace = g_tc_trace;
     a.ld32 = lg_env_flag("LG_TC_LD32", 1);
-    a.whint = (lg_env_flag("LG_L2_HINT", 0) & 2) ? tma::kL2EvictLast : 0ull;
+    a.whint = (lg_env_flag("LG_L2_HINT", 1) & 2) ? tma::kL2EvictLast : 0ull;
     const bool pf = next && lg_env_flag("LG_L2_PREFETCH", 1);
     a.pf0 = pf ? (const char*)next->p0 : nullptr; a.pfb0 = pf ? next->b0 : 0;
     a.pf1 = pf ? (const char*)next->p1 : nullptr; a.pfb1 = pf ? next->b1 : 0;

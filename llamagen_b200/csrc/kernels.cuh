@@ -31,6 +31,19 @@ struct SampleArgs {
     // continuous batching (lg_sample_rows): every image is its own request with its own RNG seed and token index
     const uint64_t* seed_rows = nullptr;   // [B] or null
     const int* step_rows = nullptr;        // [B] or null
+    // fused tail of a decode iteration (bf16 only): the CTA that picked image b's token also writes the next step's input rows b and
+    // B + b (token embedding, gpt.py:352; optionally its RMSNorm for layer 0, gpt.py:143-148) and the last CTA to finish advances the
+    // device-resident position / step counters - three dependent kernels (embed, rmsnorm, advance) fewer per token
+    const void* emb_table = nullptr;       // tok_embeddings [V][D] bf16 (null: no fused tail)
+    void* emb_h = nullptr;                 // [R][D] next step's residual stream
+    void* emb_xn = nullptr;                // [R][D] RMSNorm(h) * norm_w, or null
+    const void* emb_norm_w = nullptr;      // [D]
+    float emb_eps = 0.f;
+    int emb_D = 0;
+    int emb_rows = 0;                      // R (2B with CFG twins, else B)
+    int* adv_pos = nullptr;                // incremented once per launch by the last CTA (null: no advance)
+    int* adv_step = nullptr;
+    unsigned int* adv_ticket = nullptr;    // zero-initialised arrival counter, left at zero
 };
 int launch_sample(const SampleArgs& a, cudaStream_t st);
 
@@ -130,7 +143,9 @@ bool conv_tc_supported(int Hin, int Win, int Cin, int Cout, int ksize, int up, b
 void conv_tc_set_cta_budget(int ctas);   // > 0: persistent conv CTAs (at most `ctas`), 0: one CTA per tile, -1: LG_CONV_CTAS
 int conv_tc_make_phase_weights(const float* w_f32, bf16* out, int cout, int cin, cudaStream_t st);
 int launch_conv_tc(const bf16* in, int B, int Hin, int Win, int Cin, const bf16* weights, const float* bias, int Cout,
-                   int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st, uint8_t* out_u8 = nullptr);
+                   int ksize, int up, const bf16* residual, bf16* out_bf, float* out_nchw, cudaStream_t st, uint8_t* out_u8 = nullptr,
+                   float* gn_partial = nullptr, size_t gn_floats = 0, int* gn_splits = nullptr);   // *gn_splits > 0: the drain also wrote the
+                   // output's GroupNorm(32) partial statistics [B][*gn_splits][32][2] into gn_partial
 // gemm_tc.cu — tcgen05/TMEM/TMA weight-streaming GEMM (bf16, M <= 256)
 int gemm_tc_ksplit(int M, int N, int K);
 bool gemm_tc_supported(int M, int N, int K, int dtype);

@@ -399,11 +399,62 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
         }
     }
 
+    __shared__ int s_next;
     if (tid == 0) {
         const int pick = s_pick;
         if (a.out_idx) a.out_idx[b] = pick;
         if (a.out_seq) a.out_seq[(size_t)b * a.seq_stride + step] = pick;
-        if (a.next_tokens) a.next_tokens[b] = a.teacher ? a.teacher[(size_t)b * a.seq_stride + step] : pick;
+        const int nxt = a.teacher ? a.teacher[(size_t)b * a.seq_stride + step] : pick;
+        if (a.next_tokens) a.next_tokens[b] = nxt;
+        s_next = nxt;
+    }
+    // ---------------- fused tail: next step's input rows (embedding lookup + layer-0 RMSNorm) and the counter advance ----------
+    if (a.emb_table) {
+        __syncthreads();
+        const int D = a.emb_D;
+        const bf16* src = reinterpret_cast<const bf16*>(a.emb_table) + (size_t)s_next * D;
+        // thread -> 2 consecutive elements per pass (D even); the same token feeds the cond and the uncond row (generate.py:91)
+        for (int i = tid * 2; i < D; i += kSampleThreads * 2) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(src + i);
+            for (int row = b; row < a.emb_rows; row += B)
+                *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(a.emb_h) + (size_t)row * D + i) = w;
+        }
+        if (a.emb_xn) {
+            // sum of squares in rmsnorm_kernel's order (256 threads striding the row, then the same block reduction tree: the other
+            // 24 warps contribute zeros) so that this path and the stand-alone kernels produce bit-identical activations
+            float ss = 0.f;
+            if (tid < 256)
+                for (int i = tid; i < D; i += 256) {
+                    const float v = __bfloat162float(src[i]);
+                    ss = fmaf(v, v, ss);
+                }
+            const float tot = block_sum(ss, red);
+            const float rinv = 1.0f / sqrtf(tot / (float)D + a.emb_eps);
+            const bf16* nw = reinterpret_cast<const bf16*>(a.emb_norm_w);
+            for (int i = tid * 2; i < D; i += kSampleThreads * 2) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(src + i);
+                const uint32_t g2 = *reinterpret_cast<const uint32_t*>(nw + i);
+                // norm(x.float()).type_as(x) * weight: two bf16 roundings, as rmsnorm_kernel / residual_norm_kernel
+                const float lo = round_bf16(__uint_as_float(w << 16) * rinv) * __uint_as_float(g2 << 16);
+                const float hi = round_bf16(__uint_as_float(w & 0xffff0000u) * rinv) * __uint_as_float(g2 & 0xffff0000u);
+                __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+                for (int row = b; row < a.emb_rows; row += B)
+                    *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(a.emb_xn) + (size_t)row * D + i) = pk;
+            }
+        }
+    }
+    if (a.adv_ticket) {
+        // every CTA has read `step` (and the logits) by now; the last one to arrive moves the loop counters for the next step
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned int old = atomicAdd(a.adv_ticket, 1u);
+            if (old == gridDim.x - 1) {
+                if (a.adv_pos) *a.adv_pos += 1;
+                if (a.adv_step) *a.adv_step += 1;
+                *a.adv_ticket = 0u;
+            }
+        }
     }
 }
 

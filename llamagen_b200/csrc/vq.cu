@@ -595,6 +595,11 @@ struct VqWs {
     float *S, *gn, *Z;
     size_t bytes;
     int attn_bc;   // images per attention chunk
+    size_t gn_floats = 0;            // capacity of gn
+    // GroupNorm statistics produced by the drain of the conv that wrote `gn_src` (conv_tcw_kernel): run_gn skips its statistics pass
+    // when it is asked to normalise exactly that tensor
+    const bf16* gn_src = nullptr;
+    int gn_splits = 0;
 };
 
 size_t a256(size_t v) { return (v + 255) / 256 * 256; }
@@ -623,7 +628,14 @@ VqWs carve_vq(const lg_vq* v, char* base, int Bc, int g) {
     w.VT = (bf16*)take((size_t)Bc * N * Cd * 2);
     w.S = (float*)take((size_t)abc * N * N * 4);
     w.P = (bf16*)take((size_t)abc * N * N * 2);
-    w.gn = (float*)take((size_t)Bc * 64 * 32 * 2 * 4);
+    // statistics partials: gn_stats_kernel uses <= 64 splits per image, the conv drains one per 16x16-pixel tile of the largest output
+    {
+        int rmax = g;
+        for (int i = 0; i + 1 < c.n_mult; ++i) rmax *= 2;
+        const size_t splits = std::max<size_t>(64, (size_t)((rmax + 15) / 16) * ((rmax + 15) / 16) * 4);
+        w.gn_floats = (size_t)Bc * splits * 32 * 2;
+        w.gn = (float*)take(w.gn_floats * 4);
+    }
     w.Z = (float*)take((size_t)Bc * N * c.codebook_embed_dim * 4);   // encoder output z (fp32 NCHW) ahead of the argmin
     w.bytes = off;
     w.attn_bc = abc;
@@ -641,11 +653,14 @@ int chunk_images(const lg_vq* v, int B, int g) {
 // ---- layer launchers --------------------------------------------------------------------------------
 // up: 0 = same resolution, 1 = nearest-2x upsample folded in, 2 = Downsample (pad right/bottom, stride 2)
 int run_conv(const ConvW& cw, const bf16* in, int B, int Hin, int Win, int up, const bf16* residual, bf16* out_bf,
-             float* out_nchw, cudaStream_t st, uint8_t* out_u8 = nullptr) {
+             float* out_nchw, cudaStream_t st, uint8_t* out_u8 = nullptr, VqWs* ws = nullptr) {
+    if (ws && out_bf && ws->gn_src == out_bf) ws->gn_src = nullptr;          // the tensor the statistics described is being overwritten
     if (lg_env_flag("LG_CONV_TC", 1) && conv_tc_supported(Hin, Win, cw.cin, cw.cout, cw.k, up, out_nchw != nullptr || out_u8 != nullptr) &&
         (up != 1 || cw.w_phase)) {
+        int splits = 0;
         LG_PROF(PC_VQ_CONV, st, launch_conv_tc(in, B, Hin, Win, cw.cin, up == 1 ? cw.w_phase : cw.w, cw.bias, cw.cout, cw.k, up, residual,
-                                               out_bf, out_nchw, st, out_u8));
+                                               out_bf, out_nchw, st, out_u8, ws ? ws->gn : nullptr, ws ? ws->gn_floats : 0, ws ? &splits : nullptr));
+        if (ws && splits > 0) { ws->gn_src = out_bf; ws->gn_splits = splits; }
         return 0;
     }
     LG_REQUIRE(!out_u8, "uint8 output needs the tcgen05 conv path (Cin %% 64 == 0, LG_CONV_TC=1)");
@@ -661,12 +676,17 @@ int run_conv(const ConvW& cw, const bf16* in, int B, int Hin, int Win, int up, c
     return 0;
 }
 
-int run_gn(const NormW& nw, const bf16* x, bf16* y, int B, int HW, int swish, float* gnbuf, cudaStream_t st) {
+int run_gn(const NormW& nw, const bf16* x, bf16* y, int B, int HW, int swish, float* gnbuf, cudaStream_t st, VqWs* ws = nullptr) {
     int splits = (int)std::min<long long>(64, std::max<long long>(1, (long long)HW * nw.c / 8 / 2048));
-    prof_begin(PC_VQ_GN_STATS, st);
-    gn_stats_kernel<<<dim3(splits, B), 256, 0, st>>>(x, HW, nw.c, gnbuf);
-    prof_end(st);
-    LG_LAUNCH_CHECK();
+    if (ws && ws->gn_src == x && ws->gn_splits > 0) {
+        splits = ws->gn_splits;                  // the producing conv's drain already wrote the partial statistics of x
+    } else {
+        prof_begin(PC_VQ_GN_STATS, st);
+        gn_stats_kernel<<<dim3(splits, B), 256, 0, st>>>(x, HW, nw.c, gnbuf);
+        prof_end(st);
+        LG_LAUNCH_CHECK();
+    }
+    if (ws) ws->gn_src = nullptr;                // gnbuf is consumed below; y (and any later writer of x) invalidates it anyway
     int chunks = (int)std::min<long long>(lg_env_flag("LG_GN_CHUNKS", 256), std::max<long long>(1, (long long)HW * (nw.c / 8) / 1024));
     prof_begin(PC_VQ_GN_APPLY, st);
     gn_apply_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, gnbuf, splits, nw.gamma, nw.beta, y, HW, nw.c, swish);
@@ -678,14 +698,14 @@ int run_gn(const NormW& nw, const bf16* x, bf16* y, int B, int HW, int swish, fl
 // ResnetBlock (vq_model.py:298-314). x lives in w.X and the result is left in w.X.
 int run_res(const ResW& r, VqWs& w, int B, int H, int W, cudaStream_t st) {
     const int HW = H * W;
-    LG_TRY(run_gn(r.n1, w.X, w.T, B, HW, 1, w.gn, st));
-    LG_TRY(run_conv(r.c1, w.T, B, H, W, 0, nullptr, w.U, nullptr, st));
-    LG_TRY(run_gn(r.n2, w.U, w.T, B, HW, 1, w.gn, st));
+    LG_TRY(run_gn(r.n1, w.X, w.T, B, HW, 1, w.gn, st, &w));
+    LG_TRY(run_conv(r.c1, w.T, B, H, W, 0, nullptr, w.U, nullptr, st, nullptr, &w));
+    LG_TRY(run_gn(r.n2, w.U, w.T, B, HW, 1, w.gn, st, &w));
     if (r.has_nin) {
         LG_TRY(run_conv(r.nin, w.X, B, H, W, 0, nullptr, w.U, nullptr, st));     // shortcut -> U
-        LG_TRY(run_conv(r.c2, w.T, B, H, W, 0, w.U, w.X, nullptr, st));           // X = conv2 + shortcut
+        LG_TRY(run_conv(r.c2, w.T, B, H, W, 0, w.U, w.X, nullptr, st, nullptr, &w));  // X = conv2 + shortcut
     } else {
-        LG_TRY(run_conv(r.c2, w.T, B, H, W, 0, w.X, w.X, nullptr, st));           // in-place residual
+        LG_TRY(run_conv(r.c2, w.T, B, H, W, 0, w.X, w.X, nullptr, st, nullptr, &w));  // in-place residual
     }
     return 0;
 }
@@ -694,7 +714,7 @@ int run_res(const ResW& r, VqWs& w, int B, int H, int W, cudaStream_t st) {
 int run_attn(const AttnW& a, VqWs& w, int B, int H, int W, cudaStream_t st) {
     const int N = H * W, C = a.c;
     LG_REQUIRE(N % 8 == 0, "attention block: token count %d must be a multiple of 8", N);
-    LG_TRY(run_gn(a.norm, w.X, w.T, B, N, 0, w.gn, st));                          // hn -> T  [B*N, C]
+    LG_TRY(run_gn(a.norm, w.X, w.T, B, N, 0, w.gn, st, &w));                      // hn -> T  [B*N, C]
     {   // q | k  -> U [B*N, 2C]
         mma::DenseA al{w.T, C, 0, B * N};
         mma::BRows bw{a.qk.w, a.qk.w, 2 * C, C, 0, 2 * C};
@@ -731,7 +751,7 @@ int run_attn(const AttnW& a, VqWs& w, int B, int H, int W, cudaStream_t st) {
         }
     }
     // x = x + proj_out(O)
-    return run_conv(a.proj, w.T, B, H, W, 0, w.X, w.X, nullptr, st);
+    return run_conv(a.proj, w.T, B, H, W, 0, w.X, w.X, nullptr, st, nullptr, &w);
 }
 
 }  // namespace
@@ -887,7 +907,8 @@ static int vq_decode_impl(lg_vq* v, const int32_t* codes, int B, int grid, void*
         lookup_postquant_kernel<<<bc * grid * grid, 256, 0, st>>>(codes + (size_t)b0 * grid * grid, v->codebook, c.codebook_size,
                                                                   c.codebook_embed_dim, v->pq_w, v->pq_b, c.z_channels, w.T);
         LG_LAUNCH_CHECK();
-        LG_TRY(run_conv(v->conv_in, w.T, bc, H, W, 0, nullptr, w.X, nullptr, st));
+        w.gn_src = nullptr;
+        LG_TRY(run_conv(v->conv_in, w.T, bc, H, W, 0, nullptr, w.X, nullptr, st, nullptr, &w));
         LG_TRY(run_res(v->mid0, w, bc, H, W, st));
         LG_TRY(run_attn(v->mid1, w, bc, H, W, st));
         LG_TRY(run_res(v->mid2, w, bc, H, W, st));
@@ -898,12 +919,12 @@ static int vq_decode_impl(lg_vq* v, const int32_t* codes, int B, int grid, void*
                 if (!lv.attn.empty()) LG_TRY(run_attn(lv.attn[j], w, bc, H, W, st));
             }
             if (lv.up) {  // nearest x2 folded into the conv's gather; result -> T, then swap
-                LG_TRY(run_conv(lv.upconv, w.X, bc, H, W, 1, nullptr, w.T, nullptr, st));
+                LG_TRY(run_conv(lv.upconv, w.X, bc, H, W, 1, nullptr, w.T, nullptr, st, nullptr, &w));
                 std::swap(w.X, w.T);
                 H *= 2; W *= 2;
             }
         }
-        LG_TRY(run_gn(v->norm_out, w.X, w.T, bc, H * W, 1, w.gn, st));
+        LG_TRY(run_gn(v->norm_out, w.X, w.T, bc, H * W, 1, w.gn, st, &w));
         LG_TRY(run_conv(v->conv_out, w.T, bc, H, W, 0, nullptr, nullptr, out_nchw ? out_nchw + (size_t)b0 * out_per_img : nullptr, st,
                         out_u8 ? out_u8 + (size_t)b0 * out_per_img : nullptr));
     }
@@ -975,7 +996,7 @@ int lg_vq_encode(lg_vq* v, const float* x_nchw, int B, int H, int W, void* dev_w
                 if (!lv.attn.empty()) LG_TRY(run_attn(lv.attn[j], w, bc, h, wd, st));
             }
             if (lv.up) {
-                LG_TRY(run_conv(lv.upconv, w.X, bc, h, wd, 2, nullptr, w.T, nullptr, st));
+                LG_TRY(run_conv(lv.upconv, w.X, bc, h, wd, 2, nullptr, w.T, nullptr, st, nullptr, &w));
                 std::swap(w.X, w.T);
                 h /= 2; wd /= 2;
             }
@@ -983,7 +1004,7 @@ int lg_vq_encode(lg_vq* v, const float* x_nchw, int B, int H, int W, void* dev_w
         LG_TRY(run_res(v->enc_mid0, w, bc, h, wd, st));
         LG_TRY(run_attn(v->enc_mid1, w, bc, h, wd, st));
         LG_TRY(run_res(v->enc_mid2, w, bc, h, wd, st));
-        LG_TRY(run_gn(v->enc_norm_out, w.X, w.T, bc, h * wd, 1, w.gn, st));
+        LG_TRY(run_gn(v->enc_norm_out, w.X, w.T, bc, h * wd, 1, w.gn, st, &w));
         LG_TRY(run_conv(v->enc_conv_out, w.T, bc, h, wd, 0, nullptr, w.U, nullptr, st));
         float* z = out_z_nchw ? out_z_nchw + (size_t)b0 * ed * N : w.Z;
         LG_TRY(run_conv(v->quant_conv, w.U, bc, h, wd, 0, nullptr, nullptr, z, st));

@@ -38,7 +38,9 @@ __global__ void embed_rows_kernel(const T* __restrict__ cls_table, const T* __re
                                   const int* __restrict__ pos_rows, int B, int null_idx, int D, T* __restrict__ out) {
     lg_pdl_sync();
     const int r = blockIdx.x, b = r < B ? r : r - B;
-    const T* s = pos_rows[r] == 0 ? cls_table + (size_t)(r < B ? src[b] : null_idx) * D : tok_table + (size_t)src[b] * D;
+    // a class id outside [0, null_idx] (e.g. a stale token left in a free serving slot) reads the null class instead of running past the table
+    const int cls = (r < B && (unsigned)src[b] <= (unsigned)null_idx) ? src[b] : null_idx;
+    const T* s = pos_rows[r] == 0 ? cls_table + (size_t)cls * D : tok_table + (size_t)src[b] * D;
     T* d = out + (size_t)r * D;
     for (int i = threadIdx.x; i < D; i += blockDim.x) d[i] = s[i];
 }
@@ -70,9 +72,9 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, c
     __shared__ float red[33];
     const size_t row = (size_t)blockIdx.x * D;
     float ss = 0.f;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {      // 256 threads: the sample kernel's fused tail reduces in the same order
         const float v = TR<T>::to_f(x[row + i]);
-        ss += v * v;
+        ss = fmaf(v, v, ss);
     }
     ss = block_sum(ss, red);
     const float r = 1.0f / sqrtf(ss / (float)D + eps);

@@ -181,6 +181,8 @@ class LLM:
             rows = torch.cat([idx, idx + B]) if R == 2 * B else idx
             st["active"][rows] = 0
             st["pos"][rows] = 0
+            st["tok"][idx] = 0                                # a free slot sits at position 0 = the class branch: its input must be a valid
+                                                              # class id, not the last sampled token (which indexed past the class table)
             for i, t in zip(done, toks):
                 req = self._slots[i]
                 self._slots[i] = None
