@@ -168,7 +168,7 @@ def kernel_class(name: str) -> str:
     n = name.replace("(anonymous namespace)::", "")
     if "attn_tma" in n or "attention_kernel" in n:
         return "attention"
-    if "ConvA" in n or "conv_tc_kernel" in n:
+    if "ConvA" in n or "conv_tc_kernel" in n or "conv_tcw_kernel" in n:
         return "vq_conv_gemm"
     if "EpiVq" in n or "softmax_rows" in n:
         return "vq_attn"

@@ -63,6 +63,36 @@ def test_full_decoder_vs_oracle(name, g, B, conv, monkeypatch):
     _check_pixels(out, ref)
 
 
+@pytest.mark.parametrize("variant", ["n128_tiles", "persistent_8_ctas", "no_gn_fuse", "cta_budget_api"])
+def test_conv_kernel_variants_agree(variant, monkeypatch):
+    """The shipped decoder = weights-as-A convs (UMMA N = 256, conv_tcw_kernel) with the GroupNorm statistics in their drain. It must
+    agree with: the pixels-as-A kernel (N <= 128), the same kernels looping as 8 persistent CTAs (many tiles per CTA: ring / TMEM
+    phases carried across tiles), the stand-alone statistics pass, and the C-ABI CTA budget. Same bf16 rounding points everywhere;
+    only fp32 summation orders differ."""
+    from llamagen_b200 import VQ_models, _lib
+    torch.manual_seed(5)
+    m = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).cuda().eval()
+    codes = torch.randint(0, 16384, (2, 256), device="cuda")
+    base = m.decode_code(codes, [2, 8, 16, 16]).cpu()
+    if variant == "n128_tiles":
+        monkeypatch.setenv("LG_CONV_SWAP", "0")
+    elif variant == "persistent_8_ctas":
+        monkeypatch.setenv("LG_CONV_CTAS", "8")
+    elif variant == "no_gn_fuse":
+        monkeypatch.setenv("LG_GN_FUSE", "0")
+    else:
+        _lib.load().lg_vq_set_cta_budget(5)
+    try:
+        out = m.decode_code(codes, [2, 8, 16, 16]).cpu()
+    finally:
+        _lib.load().lg_vq_set_cta_budget(-1)
+    err = (out - base).abs()
+    if variant in ("persistent_8_ctas", "cta_budget_api"):
+        assert torch.equal(out, base)                        # same tiles, same arithmetic, only the CTA -> tile map changes
+    else:
+        assert err.max().item() <= 0.1 and err.mean().item() <= 0.004, (err.max().item(), err.mean().item())
+
+
 def test_decode_is_batch_invariant():
     """Images are independent (replica sharding relies on it): decoding a batch == decoding its halves."""
     from llamagen_b200 import VQ_models
