@@ -15,15 +15,18 @@ namespace {
 using namespace tma;
 
 #ifndef LG_ATTN_KC
-#define LG_ATTN_KC 48   // measured on B200 (GPT-L, R=128): 48 keys/stage, 3 warps, 8 CTAs/SM -> 314.9 ms/step vs 319.7 for 64/4/6
+#define LG_ATTN_KC 32   // keys per stage. Round 1 (one chain): 48 keys / 3 warps / 8 CTAs per SM beat 64 / 4 / 6 (314.9 vs 319.7 ms/step).
+                        // Round 2 (two chains, final tree): 32 keys / 2 warps / 12 CTAs per SM -> 274.7 ms/step vs 279.7 for 48 / 3 / 8
+                        // (profiles/r2_s22_sweep_attn_kc.txt): the smaller CTAs leave shared memory for the other chain's GEMM CTAs.
 #endif
 constexpr int kKC = LG_ATTN_KC;   // keys per stage (64 -> 4 warps, 6 CTAs/SM; 48 -> 3 warps, 8 CTAs/SM)
 constexpr int kStagesA = 2;       // 2 stages of K+V per CTA; contexts here are <= 1144 keys
 constexpr int kWarps = kKC / 16;  // each warp owns 16 keys of a stage
+constexpr int kDeepStages = kKC == 32 ? 8 : 6;   // few-item (batch-1) variant: the whole <= 256/288-key context is requested before the dependency wait
 #ifdef LG_ATTN_CTAS
 constexpr int kCtasPerSm64 = LG_ATTN_CTAS;
 #else
-constexpr int kCtasPerSm64 = kKC == 48 ? 8 : (kKC == 32 ? 10 : 6);
+constexpr int kCtasPerSm64 = kKC == 48 ? 8 : (kKC == 32 ? 12 : 6);
 #endif
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -69,7 +72,7 @@ struct AttnTmaArgs {
 // in EARLIER steps, so the whole KV stream is requested before the programmatic-dependency wait and overlaps the
 // QKV GEMM; one dependent kernel per layer disappears.
 template <int HD, bool FUSED, int NST, bool PAR_ = (NST > 2)>
-__global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD == 64 ? (NST > 2 ? 4 : kCtasPerSm64) : 4)) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
+__global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD == 64 ? (NST > 2 ? 4 : kCtasPerSm64) : (kKC == 32 ? 5 : 4))) attn_tma_kernel(const __grid_constant__ CUtensorMap kmap,
                                                                const __grid_constant__ CUtensorMap vmap,
                                                                const __grid_constant__ CUtensorMap kmap16,
                                                                const __grid_constant__ CUtensorMap vmap16, AttnTmaArgs a) {
@@ -152,8 +155,8 @@ __global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD
     uint32_t qa[HD / 16][2];
     if (FUSED) {
         // ---- QKV epilogue for this (row, head): slab reduce -> dtype rounding -> RoPE -> cache write / smem
-        if (threadIdx.x < 3 * HD / 4) {
-            const int sec = threadIdx.x / (HD / 4), e = (threadIdx.x % (HD / 4)) * 4;
+        for (int it = threadIdx.x; it < 3 * HD / 4; it += blockDim.x) {     // 48 / 96 items; a CTA may have only 64 threads (32-key stages)
+            const int sec = it / (HD / 4), e = (it % (HD / 4)) * 4;
             const bool live = e < hdr;                 // dims [hdr, HD) are zero padding (hdr % 4 == 0)
             const size_t N3 = (size_t)3 * D, slab = (size_t)a.R * N3;
             const float* p = a.partial + (size_t)r * N3 + (size_t)sec * D + (size_t)h * hdr + e;
@@ -167,7 +170,9 @@ __global__ void __launch_bounds__(kWarps * 32 * (PAR_ ? NST : 1), PAR_ ? 1 : (HD
             }
             float x0 = round_bf16(sv.x), x1 = round_bf16(sv.y), x2 = round_bf16(sv.z), x3 = round_bf16(sv.w);
             if (sec < 2 && live) {   // apply_rotary_emb (gpt.py:420-430): adjacent pairs, fp32, separate roundings
-                const float4 cs = cs_pre;
+                // first pass: the angles were fetched before the dependency wait; a second pass (HD = 128 on 64 threads) loads its own
+                const float4 cs = it == (int)threadIdx.x ? cs_pre
+                                                         : __ldg(reinterpret_cast<const float4*>(a.freqs + ((size_t)qpos * (hdr / 2) + (e >> 1)) * 2));
                 const float y0 = __fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y));
                 const float y1 = __fadd_rn(__fmul_rn(x1, cs.x), __fmul_rn(x0, cs.y));
                 const float y2 = __fsub_rn(__fmul_rn(x2, cs.z), __fmul_rn(x3, cs.w));
@@ -711,7 +716,7 @@ int launch_attention_tma(const AttnArgs& a, cudaStream_t st) {
     if (a.qkv_partial) {     // fused QKV epilogue
         // few (row, head) items (batch-1 latency path): a 6-stage ring holds a whole 288-key context, so every K/V byte is
         // requested before the dependency wait instead of two stages at a time
-        if (a.hd == 64 && a.R * a.H <= 2 * 148 && lg_env_flag("LG_ATTN_DEEP", 1)) return launch_t<64, true, 6>(km, vm, km16, vm16, t, st);
+        if (a.hd == 64 && a.R * a.H <= 2 * 148 && lg_env_flag("LG_ATTN_DEEP", 1)) return launch_t<64, true, kDeepStages>(km, vm, km16, vm16, t, st);
         // deeper sequential ring (A/B switch): more keys requested before the dependency wait, fewer refill round trips
         const int nst = lg_env_flag("LG_ATTN_NST", 2);
         if (a.hd == 64 && nst == 3) return launch_t<64, true, 3, false>(km, vm, km16, vm16, t, st);
