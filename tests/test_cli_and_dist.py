@@ -185,6 +185,46 @@ def test_serve_continuous_batching_host_logic():
         serve.LLM._device_step = saved
 
 
+def test_serve_free_slots_carry_valid_class_ids():
+    """Regression (round 2): a slot whose request finished sits at position 0, i.e. on the CLASS branch of the embedding lookup
+    (launch_embed_rows). Its input must be a valid class id — the last sampled token (0..16383) left there indexed far past the
+    1001-row class table on the device. The stub device step samples large token ids and checks every row it is given."""
+    import types
+    import torch
+    from llamagen_b200 import serve
+    model = types.SimpleNamespace(model_type="c2i", tok_embeddings=types.SimpleNamespace(weight=torch.zeros(1)), vocab_size=16384,
+                                  cls_token_num=1, setup_caches=lambda **kw: None)
+    seen = {"steps": 0}
+
+    def fake_device_step(self, st, params):
+        B = self.max_num_seqs
+        pos, tok = st["pos"][:B], st["tok"]
+        at_zero = pos == 0
+        assert bool(((tok[at_zero] >= 0) & (tok[at_zero] <= self.num_classes)).all()), (tok.tolist(), pos.tolist())
+        assert bool(((tok >= 0) & (tok < 16384)).all())
+        nxt = torch.full_like(tok, 16000) + torch.arange(B, dtype=tok.dtype)          # "sampled" tokens far above num_classes
+        for b in range(B):
+            st["out"][b, int(st["pos"][b])] = nxt[b]
+        st["tok"].copy_(nxt)
+        seen["steps"] += 1
+
+    serve.LLM._device_step, saved = fake_device_step, serve.LLM._device_step
+    try:
+        sp = serve.SamplingParams(top_k=10, max_tokens=4)
+        llm = serve.LLM(model, cfg_scale=4.0, num_classes=1000, max_num_seqs=3, seed=0)
+        llm.add_request([7], sp)
+        llm.add_request([8], sp)
+        for _ in range(2):
+            llm.step()
+        llm.add_request([9], sp)                       # joins mid-sequence; slots 0, 1 finish two steps before it does
+        outs = []
+        while llm.has_unfinished_requests():
+            outs += llm.step()
+        assert seen["steps"] == 6 and len(outs) == 3
+    finally:
+        serve.LLM._device_step = saved
+
+
 def test_left_pad_and_index_map_properties():
     """Property checks (hypothesis): left_pad_features == per-row rotate for arbitrary ragged lengths; the DDP index map
     i*world + rank + total (sample_c2i_ddp.py:147) is a bijection onto range(total_samples) for any world / batch."""
