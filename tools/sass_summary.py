@@ -33,7 +33,7 @@ def demangle(n):
 print("# cuobjdump -sass of the in-tree library: occurrences of selected mnemonics per kernel")
 print("# UTCHMMA = tcgen05.mma   UTMALDG = TMA tensor load   UBLKPF = cp.async.bulk.prefetch.L2   LDTM = tcgen05.ld   UTCBAR = tcgen05.commit")
 print("# HMMA = mma.sync   LDSM = ldmatrix   LDGSTS = cp.async   SYNCS = mbarrier ops   ATOMS = shared-memory atomics (TMEM allocator,")
-print("# integer histogram counters of the sampler)   ATOMG / ATOM. / RED. = global atomics: none in the library (no float atomics anywhere)")
+print("# integer histogram counters of the sampler)   ATOMG / ATOM. / RED. = global atomics: only integer control counters (grid barrier of decode_small_persistent_kernel, arrival ticket of sample_kernel's fused tail); no float atomics, none on a data path")
 rows = sorted((demangle(fn), dict(c)) for fn, c in counts.items() if c)
 for d, c in rows:
     print(f"{d}: {c}")
