@@ -276,8 +276,12 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"LlamaGen {args.gpt_model} c2i {args.image_size}px ({g}x{g} tokens), cfg={args.cfg_scale}, top_k={args.top_k}, batch={B}, "
-                                   "oracle port of the reference on host CPU (fp32, torch)", "extrapolated": True},
+            # the workload string is the one our arm prints (the driver compares the two arms' configs); what differs about this
+            # arm is said in `arm`
+            "config": {"workload": f"LlamaGen {args.gpt_model} c2i {args.image_size}px ({g}x{g} tokens), cfg={args.cfg_scale}, top_k={args.top_k}, "
+                                   f"batch={B} per GPU (R={2 * B} rows), AR sampling + VQ-16 decode to fp32 pixels",
+                       "global_batch": args.gpus * B, "arm": "oracle port of the reference on the host CPU (fp32, torch), bounded sample extrapolated to the full workload",
+                       "extrapolated": True},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "detail": detail},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
