@@ -256,3 +256,22 @@ def test_left_pad_and_index_map_properties():
 
     rotate()
     bijection()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line with the contract's keys, the same metric / unit /
+    workload string as our arm, `impl`, a `cpu_baseline` describing the run and an `e2e` that repeats the value with zero copies."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"].startswith("images/sec") and line["unit"] == "images/s"
+    assert line["higher_is_better"] is True and line["steps"] == 1 and line["n_gpus"] == 1
+    assert line["value"] > 0 and abs(line["e2e"]["value"] - line["value"]) < 1e-9
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and "decode steps" in cb["sample"]
+    assert line["config"]["workload"] == ("LlamaGen GPT-L c2i 256px (16x16 tokens), cfg=4.0, top_k=2000, batch=64 per GPU (R=128 rows), "
+                                          "AR sampling + VQ-16 decode to fp32 pixels")
